@@ -1,0 +1,157 @@
+/*
+ * avformer_b200.h — C ABI of the B200-native AVFormer transformer hot path.
+ *
+ * Drop-in boundary for the transformer-encoder stack of the reference
+ * (paths relative to the reference repo root):
+ *   models/heads.py:164-256   GELU / Residual / PreNorm / FeedForward / Attention / Transformer
+ *   models/vformer.py:245-259 SFormer token region of ResFormer.forward
+ *   models/vformer.py:270-293 TFormer
+ *   models/heads.py:258-339   AU_former
+ *   models/tformer.py:362-403 fusion head (former_AU_head)
+ *   models/loss.py:63-103     AULoss;   train.py:155  decision rule
+ *
+ * The reference has no FFI (it is pure Python/PyTorch); these are the entry points a
+ * ctypes/cffi binding of that path binds (INTEGRATION.md shows the stub).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, a negative AVF_E* code on a usage error, or a
+ *     positive cudaError_t; avf_last_error() returns a human readable message for the
+ *     calling thread.  Nothing is ever computed on the CPU: without a CUDA device every
+ *     compute entry point fails with AVF_ENODEVICE.
+ *   - activations are row-major; "tokens" are rows of a [n_seq * n_tok, dim] matrix;
+ *   - mode AVF_BF16: GEMM operands bf16 (tcgen05 / TMEM accumulators in fp32), residual stream,
+ *     LayerNorm statistics, softmax and all accumulators fp32.  mode AVF_FP32: everything fp32 on
+ *     the CUDA cores (parity mode, 1e-4 relative to the reference).
+ */
+#ifndef AVFORMER_B200_H_
+#define AVFORMER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVF_ABI_VERSION 1
+
+enum { AVF_FP32 = 0, AVF_BF16 = 1 };                 /* compute mode / storage dtype selector */
+enum { AVF_EINVAL = -1, AVF_ENODEVICE = -2, AVF_EWORKSPACE = -3, AVF_EUNSUPPORTED = -4 };
+
+/* epilogue flags of avf_linear_fwd */
+enum { AVF_EPI_BIAS = 1, AVF_EPI_GELU = 2, AVF_EPI_RESIDUAL = 4 };
+
+/* One pre-LN encoder layer (models/heads.py:246-250).  Weight matrices are [out, in] row-major
+ * exactly as nn.Linear stores them; `w_dtype` says whether they are fp32 or bf16 copies
+ * (avf_cast_f32_to_bf16 makes the latter).  Vectors are always fp32. */
+typedef struct avf_layer_weights {
+  const float* ln1_gamma;   /* [dim]            layers.L.0.fn.norm.weight          */
+  const float* ln1_beta;    /* [dim]            layers.L.0.fn.norm.bias            */
+  const void*  w_qkv;       /* [3*inner, dim]   layers.L.0.fn.fn.to_qkv.weight  (rows q|k|v, head-major) */
+  const void*  w_out;       /* [dim, inner]     layers.L.0.fn.fn.to_out.0.weight   */
+  const float* b_out;       /* [dim]            layers.L.0.fn.fn.to_out.0.bias     */
+  const float* ln2_gamma;   /* [dim]            layers.L.1.fn.norm.weight          */
+  const float* ln2_beta;    /* [dim]            layers.L.1.fn.norm.bias            */
+  const void*  w_ff1;       /* [mlp, dim]       layers.L.1.fn.fn.net.0.weight      */
+  const float* b_ff1;       /* [mlp]            layers.L.1.fn.fn.net.0.bias        */
+  const void*  w_ff2;       /* [dim, mlp]       layers.L.1.fn.fn.net.3.weight      */
+  const float* b_ff2;       /* [dim]            layers.L.1.fn.fn.net.3.bias        */
+} avf_layer_weights;
+
+/* Geometry of an encoder stack. */
+typedef struct avf_stack_shape {
+  int32_t n_seq;      /* sequences (frames for SFormer, clips otherwise) */
+  int32_t n_tok;      /* tokens per sequence: 49 / T+1 / 12               */
+  int32_t dim;        /* model dim D: 256 / 512 / 128 / 256               */
+  int32_t heads;      /* 8                                                */
+  int32_t dim_head;   /* 32 or 64                                         */
+  int32_t mlp_dim;    /* 512 / 1024 / 256 / 256                           */
+  int32_t depth;      /* layers                                           */
+} avf_stack_shape;
+
+/* ---- library / device ------------------------------------------------------------------- */
+int         avf_abi_version(void);
+const char* avf_last_error(void);
+/* SM count, compute capability major*10+minor, and whether the tcgen05 path is usable. */
+int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05);
+
+/* ---- workspace ---------------------------------------------------------------------------- */
+/* Bytes of scratch avf_encoder_stack_fwd needs for this shape/mode (replaces the implicit ATen
+ * temporaries of models/heads.py:219-239). */
+size_t avf_encoder_workspace_bytes(const avf_stack_shape* s, int mode);
+
+/* ---- a1..a5: the encoder ------------------------------------------------------------------- */
+/* x [n_seq*n_tok, ld_x] fp32 residual stream, updated IN PLACE through `depth` layers
+ * (models/heads.py:252-256).  If out != NULL the LAST layer's result is written to
+ * out [.., ld_out] instead of x (used to write the two AU_former outputs side by side into the
+ * [B,12,256] fusion input, models/avformer.py:100). */
+int avf_encoder_stack_fwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
+                          float* x, int32_t ld_x, float* out, int32_t ld_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Building blocks (exposed for tests and for callers that fuse differently). */
+/* y[r,:] = LayerNorm(x[r,:]) * gamma + beta, eps 1e-5; y is bf16 (mode BF16) or fp32. */
+int avf_layernorm_fwd(int out_mode, const float* x, int32_t ld_x, const float* gamma, const float* beta,
+                      void* y, int32_t rows, int32_t dim, void* stream);
+/* C[M,N] = epi(A[M,K] * W[N,K]^T): bias[N], tanh-GELU, + residual[M,ld_res] (fp32), in that order.
+ * mode BF16: A, W bf16, tcgen05; mode FP32: A, W fp32.  C is bf16 or fp32 per c_mode. */
+int avf_linear_fwd(int mode, const void* a, int32_t lda, const void* w, const float* bias,
+                   const float* residual, int32_t ld_res, void* c, int32_t ldc, int c_mode,
+                   int32_t m, int32_t n, int32_t k, int epilogue_flags, void* stream);
+/* softmax(q k^T * dh^-0.5) v per (sequence, head); qkv [rows, 3*heads*dh] with columns q|k|v
+ * head-major (models/heads.py:221-237); out [rows, heads*dh].  io_mode = dtype of qkv and out. */
+int avf_attention_fwd(int io_mode, const void* qkv, void* out, int32_t n_seq, int32_t n_tok,
+                      int32_t heads, int32_t dim_head, void* stream);
+
+/* ---- a6: SFormer token (un)packing, models/vformer.py:247-253 and :257-259 ---------------- */
+/* fmap [n_frames, dim, hw] (NCHW, fp32 or bf16 per io_mode) -> x [n_frames*hw, dim] fp32 + pos[hw, dim] */
+int avf_sformer_tokens_pack(int io_mode, const void* fmap, const float* pos, float* x,
+                            int32_t n_frames, int32_t dim, int32_t hw, void* stream);
+int avf_sformer_tokens_unpack(int io_mode, const float* x, void* fmap,
+                              int32_t n_frames, int32_t dim, int32_t hw, void* stream);
+/* Whole SFormer region: pack, `depth` layers, unpack (fmap_out may alias fmap_in). */
+int avf_sformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_layer_weights* layers,
+                    const float* pos, const void* fmap_in, void* fmap_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+size_t avf_sformer_workspace_bytes(const avf_stack_shape* s, int mode);
+
+/* ---- a7: TFormer glue, models/vformer.py:280-290 ------------------------------------------- */
+/* frames [n_clips*T, dim] (fp32/bf16 per io_mode) -> x [n_clips*(T+1), dim] fp32 =
+ * cat(cls, frames) + pos[T+1, dim] */
+int avf_tformer_embed(int io_mode, const void* frames, const float* cls_token, const float* pos, float* x,
+                      int32_t n_clips, int32_t n_frames, int32_t dim, void* stream);
+/* cls[c,:] = x[c*(T+1), :] */
+int avf_tformer_cls_extract(const float* x, float* cls, int32_t n_clips, int32_t n_tok, int32_t dim, void* stream);
+
+/* ---- a8: AU_former front end, models/heads.py:293-323 --------------------------------------- */
+/* emb [n_clips, 512] fp32 (row stride ld_emb, so the cls rows of a TFormer output can be read in
+ * place) -> BatchNorm1d with running statistics (eval) -> 12 Linear(512,128)+b stacked as
+ * w_cat [12*128, 512], b_cat [12*128] -> + pos[12,128] -> x [n_clips*12, 128] fp32. */
+int avf_au_former_front_fwd(int mode, const float* emb, int32_t ld_emb,
+                            const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                            const void* w_cat, const float* b_cat, const float* pos, float* x,
+                            int32_t n_clips, int32_t in_dim, int32_t emb_dim,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a9 tail + a11 + a12 -------------------------------------------------------------------- */
+/* logits[c,i] = <x[c*12+i, :], w_last[i, :]>  written to out21 [n_clips, 21] (cols 12..20 zeroed,
+ * models/avformer.py:102-105) and decisions [n_clips,12] int32 = (logit > 0) (train.py:155).
+ * Either output may be NULL. */
+int avf_au_logits_fwd(const float* x, int32_t ld_x, const float* w_last, float* out21, int32_t* decisions,
+                      int32_t n_clips, int32_t dim, void* stream);
+/* AULoss (models/loss.py:75-103): rows with labels[c,0] == -1 are dropped; pos_weight [12];
+ * loss_out[0] = mean BCE, loss_out[1] = number of valid rows.  If dlogits != NULL it receives
+ * d loss / d logits [n_clips,12] (zero on dropped rows). logits has row stride ld_logits (21). */
+int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels, const float* pos_weight,
+                    float* loss_out, float* dlogits, int32_t n_clips, void* stream);
+
+/* ---- parameter preparation ------------------------------------------------------------------ */
+int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
+int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
+/* x[r,:] += pos[r % period, :] */
+int avf_add_row_periodic(float* x, int32_t ld_x, const float* pos, int32_t rows, int32_t dim, int32_t period, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVFORMER_B200_H_ */

@@ -1,0 +1,26 @@
+"""B200-native AVFormer transformer hot path (drop-in for the reference's models/avformer.py stack).
+
+Public surface mirrors the reference's model files:
+    TwoStreamAuralVisualFormer, AudioFormer, VisualFormer          (models/avformer.py)
+    VideoModel, ResFormer, TFormer, BasicBlock                     (models/vformer.py)
+    AU_former, former_AU_head / tformer_AU_head                    (models/heads.py, models/tformer.py)
+    Transformer, Attention, FeedForward, PreNorm, Residual, GELU   (models/heads.py:164-256)
+    AULoss                                                         (models/loss.py:63-103)
+plus ``functional`` (tensor-level wrappers of the C ABI), ``dp`` (data-parallel sharding helpers)
+and ``build()``.
+"""
+from . import _lib
+from . import functional
+from ._lib import build
+from .audio import AudioModel
+from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, load_pretrain
+from .encoder import GELU, Attention, FeedForward, PreNorm, Residual, Transformer, default_precision, set_default_precision
+from .heads import AU_former, former_AU_head, tformer_AU_head
+from .loss import AULoss
+from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
+
+__all__ = [
+    "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
+    "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
+    "AULoss", "AudioModel", "functional", "build", "set_default_precision", "default_precision", "load_pretrain",
+]

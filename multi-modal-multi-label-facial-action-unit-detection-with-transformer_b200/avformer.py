@@ -1,0 +1,128 @@
+"""Drop-in AVFormer modules (models/avformer.py:37-123): same constructors, ``forward(x: dict)``,
+``.modes`` / ``.task`` attributes, loss helpers and state-dict names as the reference, so train.py:292-336
+and test_aff2.py:58-117 can use them unchanged.  Every transformer region runs in libavformer_b200.so."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import functional as AF
+from .audio import AudioModel
+from .encoder import Transformer, _check_inference
+from .heads import AU_former, former_AU_head
+from .loss import AULoss
+from .video import Dummy, VideoModel
+
+
+def load_pretrain(model, weight_path):
+    """models/avformer.py:28-35 — strips 'module.' and loads non-strictly."""
+    state = torch.load(weight_path, map_location="cpu")
+    model.load_state_dict(OrderedDict((k.replace("module.", ""), v) for k, v in state.items()), strict=False)
+
+
+class AudioFormer(nn.Module):
+    def __init__(self, modality="A", audio_pretrained=False, task="EX"):
+        super().__init__()
+        self.audio_model = AudioModel(pretrained=audio_pretrained)
+        self.task = task
+        self.modes = ["audio_features"]
+        self.audio_model.resnet.fc = Dummy()
+        self.au_head = AU_former(dropout=0.2)
+
+    def forward(self, x):
+        _check_inference(self, x)
+        feat = self.audio_model(x)
+        return self.au_head(feat)[1]
+
+
+class VisualFormer(nn.Module):
+    def __init__(self, modality="A;V", video_pretrained=True, task="EX"):
+        super().__init__()
+        self.video_model = VideoModel()
+        self.video_model.config_modality(modality)
+        self.task = task
+        self.modes = ["clip"]
+        self.au_head = AU_former(input_dim=self.video_model.fc.in_features)
+        self.video_model.fc = Dummy()
+
+    def forward(self, x):
+        _check_inference(self, x)
+        return self.au_head(self.video_model(x))[1]
+
+
+class TwoStreamAuralVisualFormer(nn.Module):
+    """TwoStreamAuralVisualFormer(modality='A;V;M', video_pretrained=True, audio_pretrained=True, task='EX').
+
+    forward(x) reads x['clip'] [B,3(+),T,112,112] and x['audio_features'] [B,1,64,1001] on the model's CUDA
+    device and returns float32 [B,21] with the 12 AU logits in [:, :12] and zeros elsewhere."""
+
+    pretrain_paths = {"video": r"K:\ABAW2022\models\pretrain\vformer.pth", "audio": r"K:\ABAW2022\models\pretrain\audio.pth"}
+
+    def __init__(self, modality="A;V;M", video_pretrained=True, audio_pretrained=True, task="EX"):
+        super().__init__()
+        self.audio_model = AudioFormer()
+        self.video_model = VisualFormer()
+        if video_pretrained:
+            load_pretrain(self.video_model, self.pretrain_paths["video"])
+            for p in self.video_model.parameters():
+                p.requires_grad = False
+        if audio_pretrained:
+            load_pretrain(self.audio_model, self.pretrain_paths["audio"])
+            for p in self.audio_model.parameters():
+                p.requires_grad = False
+        self.task = task
+        self.au_head = former_AU_head(emb_dim=256, dropout=0.2)
+        self.modes = ["clip", "audio_features"]
+        self.loss_AU = AULoss()
+
+    # -- configuration ------------------------------------------------------------------------
+    def set_precision(self, precision):
+        """'bf16' | 'fp32' | None (follow avformer_b200.set_default_precision) for every encoder stack."""
+        if precision is not None:
+            AF._mode(precision)
+        for m in self.modules():
+            if isinstance(m, Transformer):
+                m.precision = precision
+        return self
+
+    def set_clip_length(self, n_frames: int):
+        """models/vformer.py:271,299 hard-wires 16 frames; other clip lengths need a TFormer(num_patches=T)."""
+        from .video import TFormer
+        old = self.video_model.video_model.t_former
+        if old.num_patches != n_frames:
+            new = TFormer(num_patches=n_frames).to(old.cls_token.device)
+            new.spatial_transformer.precision = old.spatial_transformer.precision
+            self.video_model.video_model.t_former = new
+        return self
+
+    # -- forward ------------------------------------------------------------------------------
+    def forward(self, x):
+        audio, clip = x["audio_features"], x["clip"]
+        _check_inference(self, clip)
+        AF._cuda(clip, "x['clip']")
+        AF._cuda(audio, "x['audio_features']")
+        bs = clip.shape[0]
+        vm = self.video_model.video_model
+        # audio: ResNet-18 (torch) -> AU_former, written into columns [0,128) of the fusion input
+        fused = torch.empty((bs * 12, 256), dtype=torch.float32, device=clip.device)
+        a_feat = self.audio_model.audio_model(audio).float().contiguous()
+        self.audio_model.au_head.tokens_into(a_feat, a_feat.shape[1], bs, out=fused, ld_out=256)
+        # video: conv stages (torch) -> SFormer -> layer4/pool (torch) -> TFormer -> AU_former into columns [128,256)
+        frames = vm.s_former(clip[:, -vm.num_channels:].permute(0, 2, 1, 3, 4))
+        tok, n_clips = vm.t_former.tokens(frames)
+        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        if self.task != "AU":
+            return torch.zeros(bs, 21, device=clip.device)
+        return self.au_head.logits21_(fused, bs)
+
+    # -- loss helpers (models/avformer.py:108-123) ------------------------------------------------
+    def get_au_loss(self, y_pred, y_true):
+        return self.loss_AU(y_pred[:, :12], y_true)
+
+    def get_ex_loss(self, y_pred, y_true):
+        raise NotImplementedError("task 'EX' is outside the AU hot path this package implements")
+
+    def get_va_loss(self, y_pred, y_true):
+        raise NotImplementedError("task 'VA' is outside the AU hot path this package implements")

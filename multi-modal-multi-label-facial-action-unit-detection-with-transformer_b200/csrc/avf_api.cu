@@ -1,0 +1,291 @@
+// extern "C" surface of libavformer_b200.so (include/avformer_b200.h) and the host-side
+// orchestration of one encoder stack.  No torch types, no CPU compute path.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "avf_common.cuh"
+#include "avf_internal.h"
+
+namespace avf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("CUDA error %d (%s) at %s", int(e), cudaGetErrorString(e), what);
+  return int(e);
+}
+
+static int require_device() {
+  static int state = 0;   // 0 unknown, 1 ok, -1 none
+  if (state == 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      state = -1;
+    } else {
+      state = 1;
+    }
+  }
+  if (state < 0) {
+    set_error("no CUDA device: the AVFormer B200 path has no CPU fallback");
+    return AVF_ENODEVICE;
+  }
+  return 0;
+}
+
+static bool tcgen05_ok() {
+  static int state = 0;
+  if (state == 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess)
+      state = (major == 10) ? 1 : -1;
+    else
+      state = -1;
+  }
+  return state > 0;
+}
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+static inline size_t elt(int mode) { return mode == AVF_BF16 ? 2 : 4; }
+
+struct EncoderWs {
+  void* ln;      // [R, D]
+  void* qkv;     // [R, 3I]
+  void* attn;    // [R, I]
+  void* hid;     // [R, M]
+  size_t total;
+};
+
+static EncoderWs carve_encoder_ws(const avf_stack_shape* s, int mode, void* base) {
+  const size_t R = size_t(s->n_seq) * s->n_tok, I = size_t(s->heads) * s->dim_head, e = elt(mode);
+  uint8_t* p = static_cast<uint8_t*>(base);
+  EncoderWs w;
+  size_t off = 0;
+  w.ln = p + off;   off += align_up(R * s->dim * e);
+  w.qkv = p + off;  off += align_up(R * 3 * I * e);
+  w.attn = p + off; off += align_up(R * I * e);
+  w.hid = p + off;  off += align_up(R * s->mlp_dim * e);
+  w.total = off;
+  return w;
+}
+
+static int check_shape(const avf_stack_shape* s) {
+  AVF_REQUIRE(s != nullptr, AVF_EINVAL, "null stack shape");
+  AVF_REQUIRE(s->n_seq > 0 && s->n_tok > 0 && s->depth > 0, AVF_EINVAL, "empty stack: n_seq=%d n_tok=%d depth=%d", s->n_seq, s->n_tok, s->depth);
+  AVF_REQUIRE(s->dim % 128 == 0 && s->dim <= 1024, AVF_EUNSUPPORTED, "dim=%d must be a multiple of 128 (<= 1024)", s->dim);
+  AVF_REQUIRE(s->dim_head == 32 || s->dim_head == 64, AVF_EUNSUPPORTED, "dim_head=%d (supported: 32, 64)", s->dim_head);
+  AVF_REQUIRE((s->heads * s->dim_head) % 64 == 0 && s->mlp_dim % 64 == 0, AVF_EUNSUPPORTED, "inner=%d / mlp=%d must be multiples of 64", s->heads * s->dim_head, s->mlp_dim);
+  AVF_REQUIRE(s->n_tok <= 64, AVF_EUNSUPPORTED, "n_tok=%d: sequences longer than 64 tokens are not part of this path", s->n_tok);
+  return 0;
+}
+
+int linear(int mode, const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
+           int c_mode, int m, int n, int k, int flags, cudaStream_t st) {
+  if (mode == AVF_BF16) {
+    AVF_REQUIRE(tcgen05_ok(), AVF_EUNSUPPORTED, "bf16 mode needs an sm_100 device (tcgen05)");
+    return linear_umma(a, lda, w, bias, res, ld_res, c, ldc, c_mode, m, n, k, flags, st);
+  }
+  return linear_f32(static_cast<const float*>(a), lda, static_cast<const float*>(w), bias, res, ld_res, c, ldc, c_mode, m, n, k, flags, st);
+}
+
+static int encoder_stack(int mode, const avf_stack_shape* s, const avf_layer_weights* L, float* x, int ld_x, float* out, int ld_out,
+                         void* ws, size_t ws_bytes, cudaStream_t st) {
+  int e = check_shape(s);
+  if (e) return e;
+  AVF_REQUIRE(mode == AVF_BF16 || mode == AVF_FP32, AVF_EINVAL, "mode=%d", mode);
+  AVF_REQUIRE(L != nullptr && x != nullptr && ws != nullptr, AVF_EINVAL, "null pointer argument");
+  const EncoderWs w = carve_encoder_ws(s, mode, ws);
+  AVF_REQUIRE(ws_bytes >= w.total, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, w.total);
+  const int R = s->n_seq * s->n_tok, D = s->dim, I = s->heads * s->dim_head, M = s->mlp_dim;
+  for (int l = 0; l < s->depth; ++l) {
+    const avf_layer_weights& W = L[l];
+    // x + to_out(attn(to_qkv(LN(x))))                                     models/heads.py:175,185,219-239
+    if ((e = layernorm(mode, x, ld_x, W.ln1_gamma, W.ln1_beta, w.ln, R, D, st))) return e;
+    if ((e = linear(mode, w.ln, D, W.w_qkv, nullptr, nullptr, 0, w.qkv, 3 * I, mode, R, 3 * I, D, 0, st))) return e;
+    if ((e = attention_small(mode, w.qkv, w.attn, s->n_seq, s->n_tok, s->heads, s->dim_head, st))) return e;
+    if ((e = linear(mode, w.attn, I, W.w_out, W.b_out, x, ld_x, x, ld_x, AVF_FP32, R, D, I, AVF_EPI_BIAS | AVF_EPI_RESIDUAL, st))) return e;
+    // x + W2 gelu(W1 LN(x) + b1) + b2                                     models/heads.py:188-200
+    if ((e = layernorm(mode, x, ld_x, W.ln2_gamma, W.ln2_beta, w.ln, R, D, st))) return e;
+    if ((e = linear(mode, w.ln, D, W.w_ff1, W.b_ff1, nullptr, 0, w.hid, M, mode, R, M, D, AVF_EPI_BIAS | AVF_EPI_GELU, st))) return e;
+    const bool last = (l == s->depth - 1) && out != nullptr;
+    if ((e = linear(mode, w.hid, M, W.w_ff2, W.b_ff2, x, ld_x, last ? out : x, last ? ld_out : ld_x, AVF_FP32, R, D, M,
+                    AVF_EPI_BIAS | AVF_EPI_RESIDUAL, st)))
+      return e;
+  }
+  return 0;
+}
+
+}  // namespace avf
+
+using namespace avf;
+
+extern "C" {
+
+int avf_abi_version(void) { return AVF_ABI_VERSION; }
+
+const char* avf_last_error(void) { return g_err; }
+
+int avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05) {
+  int e = require_device();
+  if (e) return e;
+  int dev = 0, sms = 0, major = 0, minor = 0;
+  AVF_CUDA(cudaGetDevice(&dev));
+  AVF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  AVF_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  AVF_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc) *cc = major * 10 + minor;
+  if (has_tcgen05) *has_tcgen05 = major == 10 ? 1 : 0;
+  return 0;
+}
+
+size_t avf_encoder_workspace_bytes(const avf_stack_shape* s, int mode) {
+  if (s == nullptr || s->n_seq <= 0 || s->n_tok <= 0) return 0;
+  return carve_encoder_ws(s, mode, nullptr).total;
+}
+
+int avf_encoder_stack_fwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers, float* x, int32_t ld_x, float* out,
+                          int32_t ld_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  return encoder_stack(mode, s, layers, x, ld_x, out, ld_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int avf_layernorm_fwd(int out_mode, const float* x, int32_t ld_x, const float* gamma, const float* beta, void* y, int32_t rows,
+                      int32_t dim, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(x && gamma && beta && y, AVF_EINVAL, "layernorm: null pointer");
+  return layernorm(out_mode, x, ld_x, gamma, beta, y, rows, dim, static_cast<cudaStream_t>(stream));
+}
+
+int avf_linear_fwd(int mode, const void* a, int32_t lda, const void* w, const float* bias, const float* residual, int32_t ld_res,
+                   void* c, int32_t ldc, int c_mode, int32_t m, int32_t n, int32_t k, int epilogue_flags, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(a && w && c, AVF_EINVAL, "linear: null pointer");
+  AVF_REQUIRE(!(epilogue_flags & AVF_EPI_BIAS) || bias, AVF_EINVAL, "linear: bias flag without bias");
+  AVF_REQUIRE(!(epilogue_flags & AVF_EPI_RESIDUAL) || residual, AVF_EINVAL, "linear: residual flag without residual");
+  return linear(mode, a, lda, w, bias, residual, ld_res, c, ldc, c_mode, m, n, k, epilogue_flags, static_cast<cudaStream_t>(stream));
+}
+
+int avf_attention_fwd(int io_mode, const void* qkv, void* out, int32_t n_seq, int32_t n_tok, int32_t heads, int32_t dim_head, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(qkv && out, AVF_EINVAL, "attention: null pointer");
+  return attention_small(io_mode, qkv, out, n_seq, n_tok, heads, dim_head, static_cast<cudaStream_t>(stream));
+}
+
+int avf_sformer_tokens_pack(int io_mode, const void* fmap, const float* pos, float* x, int32_t n_frames, int32_t dim, int32_t hw, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(fmap && pos && x, AVF_EINVAL, "sformer_tokens_pack: null pointer");
+  return sformer_pack(io_mode, fmap, pos, x, n_frames, dim, hw, static_cast<cudaStream_t>(stream));
+}
+
+int avf_sformer_tokens_unpack(int io_mode, const float* x, void* fmap, int32_t n_frames, int32_t dim, int32_t hw, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(fmap && x, AVF_EINVAL, "sformer_tokens_unpack: null pointer");
+  return sformer_unpack(io_mode, x, fmap, n_frames, dim, hw, static_cast<cudaStream_t>(stream));
+}
+
+size_t avf_sformer_workspace_bytes(const avf_stack_shape* s, int mode) {
+  if (s == nullptr || s->n_seq <= 0 || s->n_tok <= 0) return 0;
+  return align_up(size_t(s->n_seq) * s->n_tok * s->dim * 4) + carve_encoder_ws(s, mode, nullptr).total;
+}
+
+int avf_sformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_layer_weights* layers, const float* pos,
+                    const void* fmap_in, void* fmap_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  if ((e = check_shape(s))) return e;
+  AVF_REQUIRE(layers && pos && fmap_in && fmap_out && workspace, AVF_EINVAL, "sformer_fwd: null pointer");
+  const size_t need = avf_sformer_workspace_bytes(s, mode);
+  AVF_REQUIRE(workspace_bytes >= need, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* x = static_cast<float*>(workspace);
+  const size_t xbytes = align_up(size_t(s->n_seq) * s->n_tok * s->dim * 4);
+  if ((e = sformer_pack(io_mode, fmap_in, pos, x, s->n_seq, s->dim, s->n_tok, st))) return e;
+  if ((e = encoder_stack(mode, s, layers, x, s->dim, nullptr, 0, static_cast<uint8_t*>(workspace) + xbytes, workspace_bytes - xbytes, st))) return e;
+  return sformer_unpack(io_mode, x, fmap_out, s->n_seq, s->dim, s->n_tok, st);
+}
+
+int avf_tformer_embed(int io_mode, const void* frames, const float* cls_token, const float* pos, float* x, int32_t n_clips,
+                      int32_t n_frames, int32_t dim, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(frames && cls_token && pos && x, AVF_EINVAL, "tformer_embed: null pointer");
+  return tformer_embed(io_mode, frames, cls_token, pos, x, n_clips, n_frames, dim, static_cast<cudaStream_t>(stream));
+}
+
+int avf_tformer_cls_extract(const float* x, float* cls, int32_t n_clips, int32_t n_tok, int32_t dim, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(x && cls, AVF_EINVAL, "tformer_cls_extract: null pointer");
+  return rows_gather(x, size_t(n_tok) * dim, cls, n_clips, dim, static_cast<cudaStream_t>(stream));
+}
+
+int avf_au_former_front_fwd(int mode, const float* emb, int32_t ld_emb, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                            const float* bn_var, const void* w_cat, const float* b_cat, const float* pos, float* x, int32_t n_clips,
+                            int32_t in_dim, int32_t emb_dim, void* workspace, size_t workspace_bytes, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(emb && bn_gamma && bn_beta && bn_mean && bn_var && w_cat && b_cat && pos && x && workspace, AVF_EINVAL, "au_former_front: null pointer");
+  AVF_REQUIRE(n_clips > 0 && in_dim > 0 && emb_dim > 0, AVF_EINVAL, "au_former_front: n_clips=%d", n_clips);
+  const size_t need = align_up(size_t(n_clips) * in_dim * elt(mode));
+  AVF_REQUIRE(workspace_bytes >= need, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((e = bn_rows(mode, emb, ld_emb, bn_gamma, bn_beta, bn_mean, bn_var, workspace, n_clips, in_dim, st))) return e;
+  // [n_clips, 12*emb_dim] row-major IS [n_clips*12, emb_dim]: token i = AU_linear_p{i+1}  (models/heads.py:294-319)
+  if ((e = linear(mode, workspace, in_dim, w_cat, b_cat, nullptr, 0, x, 12 * emb_dim, AVF_FP32, n_clips, 12 * emb_dim, in_dim, AVF_EPI_BIAS, st))) return e;
+  return add_row_periodic(x, emb_dim, pos, n_clips * 12, emb_dim, 12, st);
+}
+
+int avf_au_logits_fwd(const float* x, int32_t ld_x, const float* w_last, float* out21, int32_t* decisions, int32_t n_clips, int32_t dim, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(x && w_last, AVF_EINVAL, "au_logits: null pointer");
+  return au_logits(x, ld_x, w_last, out21, decisions, n_clips, dim, static_cast<cudaStream_t>(stream));
+}
+
+int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels, const float* pos_weight, float* loss_out, float* dlogits,
+                    int32_t n_clips, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(logits && labels && pos_weight && loss_out, AVF_EINVAL, "au_bce_loss: null pointer");
+  return au_bce(logits, ld_logits, labels, pos_weight, loss_out, dlogits, n_clips, static_cast<cudaStream_t>(stream));
+}
+
+int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE((src && dst) || n == 0, AVF_EINVAL, "cast: null pointer");
+  return cast_f32_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE((src && dst) || n == 0, AVF_EINVAL, "cast: null pointer");
+  return cast_bf16_f32(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+
+int avf_add_row_periodic(float* x, int32_t ld_x, const float* pos, int32_t rows, int32_t dim, int32_t period, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(x && pos, AVF_EINVAL, "add_row_periodic: null pointer");
+  return add_row_periodic(x, ld_x, pos, rows, dim, period, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// Internal C++ launchers shared between the translation units of libavformer_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace avf {
+
+// avf_rowops.cu
+int layernorm(int out_mode, const float* x, int ld_x, const float* g, const float* b, void* y, int rows, int dim, cudaStream_t st);
+int bn_rows(int out_mode, const float* x, int ld_x, const float* g, const float* b, const float* mean, const float* var, void* y,
+            int rows, int dim, cudaStream_t st);
+int sformer_pack(int io_mode, const void* fmap, const float* pos, float* x, int n_frames, int dim, int hw, cudaStream_t st);
+int sformer_unpack(int io_mode, const float* x, void* fmap, int n_frames, int dim, int hw, cudaStream_t st);
+int tformer_embed(int io_mode, const void* frames, const float* cls, const float* pos, float* x, int n_clips, int T, int dim, cudaStream_t st);
+int rows_gather(const float* x, size_t src_row_stride, float* y, int rows, int dim, cudaStream_t st);
+int add_row_periodic(float* x, int ld_x, const float* pos, int rows, int dim, int period, cudaStream_t st);
+int cast_f32_bf16(const float* s, void* d, size_t n, cudaStream_t st);
+int cast_bf16_f32(const void* s, float* d, size_t n, cudaStream_t st);
+int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* decisions, int n_clips, int dim, cudaStream_t st);
+int au_bce(const float* logits, int ld, const float* labels, const float* pw, float* loss_out, float* dlogits, int n_clips, cudaStream_t st);
+
+// avf_simt.cu
+int linear_f32(const float* a, int lda, const float* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
+               int c_mode, int m, int n, int k, int flags, cudaStream_t st);
+int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+
+// avf_gemm_umma.cu
+int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
+                int c_mode, int m, int n, int k, int flags, cudaStream_t st);
+
+}  // namespace avf

@@ -1,0 +1,161 @@
+"""Pre-LN ViT encoder stack with the reference's module tree and state-dict names
+(models/heads.py:164-256 and its byte-identical copies in vformer.py / tformer.py), executed by the
+hand-written sm_100a kernels behind the C ABI.
+
+The module tree exists to own parameters under the reference's names:
+
+    layers.L.0.fn.norm.{weight,bias}      layers.L.0.fn.fn.to_qkv.weight
+    layers.L.0.fn.fn.to_out.0.{weight,bias}
+    layers.L.1.fn.norm.{weight,bias}      layers.L.1.fn.fn.net.{0,3}.{weight,bias}
+
+``Transformer.forward`` does not walk that tree: it hands the whole stack to
+``avf_encoder_stack_fwd``.  The sub-modules keep a working ``forward`` built from the library's
+building blocks so that they can be called on their own like the reference's.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import functional as AF
+
+_DEFAULT_PRECISION = "bf16"
+
+
+def set_default_precision(precision: str) -> None:
+    """'bf16' (tcgen05 tensor cores, fp32 residual/statistics) or 'fp32' (CUDA-core parity mode)."""
+    global _DEFAULT_PRECISION
+    AF._mode(precision)
+    _DEFAULT_PRECISION = precision
+
+
+def default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+def _check_inference(module: nn.Module, x: torch.Tensor) -> None:
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        if not getattr(module, "_avf_allow_no_grad_path", False):
+            raise NotImplementedError(
+                "avformer_b200: this build runs the encoder forward only; call it under torch.no_grad() "
+                "(the backward kernels are not part of this milestone)")
+
+
+class GELU(nn.Module):
+    """tanh-GELU (models/heads.py:164-166); fused into the MLP1 epilogue when run through Transformer."""
+
+    def forward(self, x):
+        raise RuntimeError("GELU is fused into FeedForward's first linear; call FeedForward or Transformer")
+
+
+class Residual(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, **kw):
+        return self.fn(x, **kw) + x
+
+
+class PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.fn = fn
+
+    def forward(self, x, **kw):
+        prec = default_precision()
+        y = AF.layernorm_fwd(x, self.norm.weight, self.norm.bias, prec)
+        return self.fn(y.view(x.shape), **kw)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden_dim, dropout=0.0):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden_dim), GELU(), nn.Dropout(dropout), nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+    def forward(self, x):
+        prec = default_precision()
+        cast = AF.to_bf16 if prec == "bf16" else (lambda t: t.detach().float())
+        a = x.reshape(-1, x.shape[-1])
+        a = a if a.dtype == (torch.bfloat16 if prec == "bf16" else torch.float32) else cast(a)
+        h = AF.linear_fwd(a, cast(self.net[0].weight), self.net[0].bias, gelu=True, out_dtype=a.dtype, precision=prec)
+        y = AF.linear_fwd(h, cast(self.net[3].weight), self.net[3].bias, out_dtype=torch.float32, precision=prec)
+        return y.view(*x.shape[:-1], -1)
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads, self.dim_head = heads, dim_head
+        self.scale = dim_head ** -0.5
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        project_out = not (heads == 1 and dim_head == dim)
+        self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout)) if project_out else nn.Identity()
+
+    def forward(self, x, mask=None):
+        if mask is not None:
+            raise NotImplementedError("attention masks are never passed on the AVFormer path (models/heads.py:225-232 is dead code)")
+        prec = default_precision()
+        cast = AF.to_bf16 if prec == "bf16" else (lambda t: t.detach().float())
+        b, n, _ = x.shape
+        a = x.reshape(b * n, -1)
+        a = a if a.dtype == (torch.bfloat16 if prec == "bf16" else torch.float32) else cast(a)
+        qkv = AF.linear_fwd(a, cast(self.to_qkv.weight), out_dtype=a.dtype, precision=prec)
+        o = AF.attention_fwd(qkv, b, n, self.heads, self.dim_head)
+        if isinstance(self.to_out, nn.Identity):
+            return AF.to_f32(o).view(b, n, -1) if o.dtype != torch.float32 else o.view(b, n, -1)
+        y = AF.linear_fwd(o, cast(self.to_out[0].weight), self.to_out[0].bias, out_dtype=torch.float32, precision=prec)
+        return y.view(b, n, -1)
+
+
+class Transformer(nn.Module):
+    """Transformer(dim, depth, heads, dim_head, mlp_dim, dropout=0.) — models/heads.py:242-256."""
+
+    def __init__(self, dim, depth, heads, dim_head, mlp_dim, dropout=0.0):
+        super().__init__()
+        self.dim, self.depth, self.heads, self.dim_head, self.mlp_dim, self.dropout = dim, depth, heads, dim_head, mlp_dim, dropout
+        self.layers = nn.ModuleList([
+            nn.ModuleList([Residual(PreNorm(dim, Attention(dim, heads=heads, dim_head=dim_head, dropout=dropout))),
+                           Residual(PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout)))])
+            for _ in range(depth)])
+        self.precision: Optional[str] = None       # None -> default_precision()
+        self._packed: Optional[AF.PackedStack] = None
+
+    # -- weights -------------------------------------------------------------------------------
+    def _layer_tensors(self):
+        for attn, ff in self.layers:
+            a, f = attn.fn, ff.fn
+            yield dict(ln1_gamma=a.norm.weight, ln1_beta=a.norm.bias, w_qkv=a.fn.to_qkv.weight,
+                       w_out=a.fn.to_out[0].weight, b_out=a.fn.to_out[0].bias,
+                       ln2_gamma=f.norm.weight, ln2_beta=f.norm.bias,
+                       w_ff1=f.fn.net[0].weight, b_ff1=f.fn.net[0].bias, w_ff2=f.fn.net[3].weight, b_ff2=f.fn.net[3].bias)
+
+    def packed(self) -> AF.PackedStack:
+        mode = AF._mode(self.precision or default_precision())
+        p = self._packed
+        if p is None or p.mode != mode or p.stale():
+            p = self._packed = AF.PackedStack(list(self._layer_tensors()), mode)
+        return p
+
+    def shape(self, n_seq: int, n_tok: int):
+        return AF.make_shape(n_seq, n_tok, self.dim, self.heads, self.dim_head, self.mlp_dim, self.depth)
+
+    # -- forward -------------------------------------------------------------------------------
+    def forward_(self, x2d: torch.Tensor, n_seq: int, n_tok: int, out: Optional[torch.Tensor] = None, ld_out: int = 0) -> torch.Tensor:
+        """In place on an fp32 residual stream [n_seq*n_tok, dim]."""
+        if self.training and self.dropout > 0.0:
+            raise NotImplementedError("avformer_b200: dropout>0 in train() mode is not implemented (eval() or dropout=0)")
+        return AF.encoder_stack_fwd_(x2d, self.packed(), self.shape(n_seq, n_tok), out, ld_out)
+
+    def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:
+        if mask is not None:
+            raise NotImplementedError("attention masks are never passed on the AVFormer path (models/heads.py:225-232 is dead code)")
+        _check_inference(self, x)
+        AF._cuda(x, "x")
+        b, n, d = x.shape
+        y = x.detach().float().reshape(b * n, d).clone()
+        return self.forward_(y, b, n).view(b, n, d)

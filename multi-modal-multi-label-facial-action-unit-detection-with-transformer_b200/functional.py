@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI (include/avformer_b200.h).
+
+torch is used for device memory, streams and parameter storage only; every arithmetic step of the
+hot path happens inside libavformer_b200.so.  All wrappers raise on CPU tensors — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AVF_BF16, AVF_FP32, LayerWeights, StackShape, check
+
+PRECISIONS = {"fp32": AVF_FP32, "bf16": AVF_BF16}
+
+
+def _mode(precision) -> int:
+    if isinstance(precision, int):
+        return precision
+    try:
+        return PRECISIONS[precision]
+    except KeyError:
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}") from None
+
+
+def _io_mode(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return AVF_FP32
+    if t.dtype == torch.bfloat16:
+        return AVF_BF16
+    raise TypeError(f"avformer_b200: unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"avformer_b200: '{name}' is on {t.device}; the B200 path has no CPU fallback")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# workspace: one growable byte buffer per (device, stream)
+# ------------------------------------------------------------------------------------------------
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter preparation
+# ------------------------------------------------------------------------------------------------
+def to_bf16(src: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 copy made by the library's own cast kernel."""
+    src = _f32c(_cuda(src, "src"))
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(_lib.lib().avf_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_f32_to_bf16")
+    return dst
+
+
+def to_f32(src: torch.Tensor) -> torch.Tensor:
+    src = _cuda(src, "src").contiguous()
+    dst = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    check(_lib.lib().avf_cast_bf16_to_f32(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_bf16_to_f32")
+    return dst
+
+
+class PackedStack:
+    """Device-side weight table of one encoder stack: an array of avf_layer_weights plus the tensors
+    that keep the pointers alive.  ``sources`` are the live nn.Parameters; ``stale()`` compares their
+    versions so an optimizer step or load_state_dict triggers a re-pack."""
+
+    def __init__(self, layers: Sequence[Dict[str, torch.Tensor]], mode: int):
+        self.mode = mode
+        self.depth = len(layers)
+        self.keep: List[torch.Tensor] = []
+        self.sources: List[torch.Tensor] = []
+        self.array = (LayerWeights * self.depth)()
+        mats = ("w_qkv", "w_out", "w_ff1", "w_ff2")
+        for i, lw in enumerate(layers):
+            for name, _ in LayerWeights._fields_:
+                src = lw[name]
+                self.sources.append(src)
+                t = _f32c(_cuda(src, name))
+                if name in mats and mode == AVF_BF16:
+                    t = to_bf16(t)
+                self.keep.append(t)
+                setattr(self.array[i], name, t.data_ptr())
+        self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+
+    def stale(self) -> bool:
+        return any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+
+
+# ------------------------------------------------------------------------------------------------
+# a1..a5
+# ------------------------------------------------------------------------------------------------
+def make_shape(n_seq, n_tok, dim, heads, dim_head, mlp_dim, depth) -> StackShape:
+    return StackShape(n_seq, n_tok, dim, heads, dim_head, mlp_dim, depth)
+
+
+def encoder_stack_fwd_(x: torch.Tensor, packed: PackedStack, shape: StackShape, out: Optional[torch.Tensor] = None,
+                       ld_out: int = 0) -> torch.Tensor:
+    """In-place encoder stack on the fp32 residual stream x [n_seq*n_tok, dim] (row stride = x.stride(0)).
+    If ``out`` is given the last layer writes there (row stride ld_out) instead."""
+    _cuda(x, "x")
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise TypeError("encoder_stack_fwd_: x must be a float32 residual stream with unit column stride")
+    L = _lib.lib()
+    need = L.avf_encoder_workspace_bytes(ctypes.byref(shape), packed.mode)
+    ws = workspace(need, x.device)
+    check(L.avf_encoder_stack_fwd(packed.mode, ctypes.byref(shape), packed.array, _ptr(x), x.stride(0), _ptr(out), ld_out,
+                                  _ptr(ws), ws.numel(), _stream()), "encoder_stack_fwd")
+    return x if out is None else out
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, precision="bf16") -> torch.Tensor:
+    x = _f32c(_cuda(x, "x"))
+    rows, dim = x.numel() // x.shape[-1], x.shape[-1]
+    mode = _mode(precision)
+    y = torch.empty(x.shape, dtype=torch.bfloat16 if mode == AVF_BF16 else torch.float32, device=x.device)
+    check(_lib.lib().avf_layernorm_fwd(mode, _ptr(x), dim, _ptr(_f32c(gamma)), _ptr(_f32c(beta)), _ptr(y), rows, dim, _stream()), "layernorm_fwd")
+    return y
+
+
+def linear_fwd(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+               gelu: bool = False, out_dtype: torch.dtype = torch.float32, precision="bf16") -> torch.Tensor:
+    """epi(a @ w.T): a [M,K], w [N,K] (both bf16 for precision 'bf16', both fp32 for 'fp32')."""
+    mode = _mode(precision)
+    want = torch.bfloat16 if mode == AVF_BF16 else torch.float32
+    _cuda(a, "a")
+    if a.dtype != want or w.dtype != want:
+        raise TypeError(f"linear_fwd({precision}): operands must be {want}, got {a.dtype} / {w.dtype}")
+    a, w = a.contiguous(), w.contiguous()
+    m, k = a.shape
+    n = w.shape[0]
+    c = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    flags = (1 if bias is not None else 0) | (2 if gelu else 0) | (4 if residual is not None else 0)
+    if residual is not None:
+        residual = _f32c(residual)
+    if bias is not None:
+        bias = _f32c(bias)
+    check(_lib.lib().avf_linear_fwd(mode, _ptr(a), k, _ptr(w), _ptr(bias), _ptr(residual), n, _ptr(c), n, _io_mode(c), m, n, k, flags,
+                                    _stream()), "linear_fwd")
+    return c
+
+
+def attention_fwd(qkv: torch.Tensor, n_seq: int, n_tok: int, heads: int, dim_head: int) -> torch.Tensor:
+    qkv = _cuda(qkv, "qkv").contiguous()
+    out = torch.empty((n_seq * n_tok, heads * dim_head), dtype=qkv.dtype, device=qkv.device)
+    check(_lib.lib().avf_attention_fwd(_io_mode(qkv), _ptr(qkv), _ptr(out), n_seq, n_tok, heads, dim_head, _stream()), "attention_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a6 / a7 / a8 / a9 / a11 / a12
+# ------------------------------------------------------------------------------------------------
+def sformer_fwd(fmap: torch.Tensor, pos: torch.Tensor, packed: PackedStack, heads: int, dim_head: int, mlp_dim: int) -> torch.Tensor:
+    """models/vformer.py:245-259 on a stage-3 map [F, C, H, W] (fp32 or bf16, NCHW-contiguous)."""
+    fmap = _cuda(fmap, "fmap").contiguous()
+    F_, C, H, W = fmap.shape
+    shape = make_shape(F_, H * W, C, heads, dim_head, mlp_dim, packed.depth)
+    L = _lib.lib()
+    need = L.avf_sformer_workspace_bytes(ctypes.byref(shape), packed.mode)
+    ws = workspace(need, fmap.device)
+    out = torch.empty_like(fmap)
+    check(L.avf_sformer_fwd(packed.mode, _io_mode(fmap), ctypes.byref(shape), packed.array, _ptr(_f32c(pos)), _ptr(fmap), _ptr(out),
+                            _ptr(ws), ws.numel(), _stream()), "sformer_fwd")
+    return out
+
+
+def tformer_embed(frames: torch.Tensor, cls_token: torch.Tensor, pos: torch.Tensor, n_frames: int) -> torch.Tensor:
+    frames = _cuda(frames, "frames").contiguous()
+    dim = frames.shape[-1]
+    n_clips = frames.numel() // (n_frames * dim)
+    x = torch.empty((n_clips * (n_frames + 1), dim), dtype=torch.float32, device=frames.device)
+    check(_lib.lib().avf_tformer_embed(_io_mode(frames), _ptr(frames), _ptr(_f32c(cls_token)), _ptr(_f32c(pos)), _ptr(x), n_clips, n_frames,
+                                       dim, _stream()), "tformer_embed")
+    return x
+
+
+def tformer_cls_extract(x: torch.Tensor, n_clips: int, n_tok: int) -> torch.Tensor:
+    dim = x.shape[-1]
+    cls = torch.empty((n_clips, dim), dtype=torch.float32, device=x.device)
+    check(_lib.lib().avf_tformer_cls_extract(_ptr(x), _ptr(cls), n_clips, n_tok, dim, _stream()), "tformer_cls_extract")
+    return cls
+
+
+def au_former_front(emb: torch.Tensor, ld_emb: int, n_clips: int, bn: Sequence[torch.Tensor], w_cat: torch.Tensor, b_cat: torch.Tensor,
+                    pos: torch.Tensor, mode: int) -> torch.Tensor:
+    """BN(eval) + 12 stacked Linear(512,128) + pos -> fp32 tokens [n_clips*12, 128] (models/heads.py:293-323)."""
+    _cuda(emb, "emb")
+    in_dim, emb_dim = w_cat.shape[1], w_cat.shape[0] // 12
+    x = torch.empty((n_clips * 12, emb_dim), dtype=torch.float32, device=emb.device)
+    ws = workspace(n_clips * in_dim * 4 + 256, emb.device)
+    g, b, mu, var = (_f32c(t) for t in bn)
+    check(_lib.lib().avf_au_former_front_fwd(mode, _ptr(emb), ld_emb, _ptr(g), _ptr(b), _ptr(mu), _ptr(var), _ptr(w_cat), _ptr(b_cat),
+                                             _ptr(_f32c(pos)), _ptr(x), n_clips, in_dim, emb_dim, _ptr(ws), ws.numel(), _stream()),
+          "au_former_front_fwd")
+    return x
+
+
+def au_logits(x: torch.Tensor, w_last: torch.Tensor, n_clips: int, want_decisions: bool = False):
+    """Tail of the fusion head: [B,21] zero-padded output (+ int32 decisions)."""
+    _cuda(x, "x")
+    out = torch.empty((n_clips, 21), dtype=torch.float32, device=x.device)
+    dec = torch.empty((n_clips, 12), dtype=torch.int32, device=x.device) if want_decisions else None
+    check(_lib.lib().avf_au_logits_fwd(_ptr(x), x.stride(0), _ptr(w_last), _ptr(out), _ptr(dec), n_clips, x.shape[-1], _stream()), "au_logits_fwd")
+    return (out, dec) if want_decisions else out
+
+
+def au_bce_loss(y_pred: torch.Tensor, y_true: torch.Tensor, pos_weight: torch.Tensor, want_grad: bool = False):
+    """AULoss (models/loss.py:75-103) on logits y_pred[:, :12]; returns (loss scalar tensor, n_valid, dlogits|None)."""
+    _cuda(y_pred, "y_pred")
+    if y_pred.dtype != torch.float32 or y_pred.stride(-1) != 1:
+        y_pred = y_pred.float().contiguous()
+    y_true = _f32c(_cuda(y_true, "y_true"))
+    n = y_pred.shape[0]
+    res = torch.empty(2, dtype=torch.float32, device=y_pred.device)
+    grad = torch.empty((n, 12), dtype=torch.float32, device=y_pred.device) if want_grad else None
+    check(_lib.lib().avf_au_bce_loss(_ptr(y_pred), y_pred.stride(0), _ptr(y_true), _ptr(_f32c(pos_weight)), _ptr(res), _ptr(grad), n, _stream()),
+          "au_bce_loss")
+    return res[0], res[1], grad
+
+
+def add_row_periodic_(x: torch.Tensor, pos: torch.Tensor, period: int) -> torch.Tensor:
+    check(_lib.lib().avf_add_row_periodic(_ptr(x), x.stride(0), _ptr(_f32c(pos)), x.shape[0], x.shape[1], period, _stream()), "add_row_periodic")
+    return x
+
+
+def device_info() -> Dict[str, int]:
+    a, b, c = _lib._i32(), _lib._i32(), _lib._i32()
+    check(_lib.lib().avf_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "device_info")
+    return {"sm_count": a.value, "cc": b.value, "has_tcgen05": c.value}

@@ -1,0 +1,85 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/avformer_b200.h declares,
+refuses to compute without a device, and the drop-in modules honour the reference's state-dict contract."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import avformer_b200 as A
+from oracle import avformer_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "avformer_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(avf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(A._lib.build())
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/avformer_b200.h but not exported"
+    assert set(names) == set(A._lib.SIGNATURES), "ctypes signature table and header disagree"
+    assert A._lib.lib().avf_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_device_means_error_not_fallback():
+    L = A._lib.lib()
+    a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    assert L.avf_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == -2          # AVF_ENODEVICE
+    assert b"no CPU fallback" in L.avf_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        A.functional.to_bf16(torch.zeros(8))
+    m = A.Transformer(128, 1, 8, 32, 256)
+    with pytest.raises(RuntimeError, match="no CPU fallback"), torch.no_grad():
+        m(torch.zeros(1, 12, 128))
+
+
+def test_state_dict_contract_matches_reference_names():
+    m = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU")
+    spec = {k: s for k, s, _ in O.state_dict_spec(16)}
+    sd = m.state_dict()
+    assert set(sd) == set(spec) and len(sd) == 462
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(spec[k]), k
+    res = m.load_state_dict(O.make_state_dict(5, 16), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert m.modes == ["clip", "audio_features"] and m.task == "AU"
+    assert sum(p.numel() for p in m.parameters()) == 32_764_416
+    # dropout placement of the reference: 0.2 in the audio AU_former and the fusion head, 0 elsewhere
+    assert m.audio_model.au_head.corr_transformer.dropout == 0.2 and m.au_head.corr_transformer.dropout == 0.2
+    assert m.video_model.au_head.corr_transformer.dropout == 0.0
+    # other clip lengths need a TFormer(num_patches=T) (models/vformer.py:271)
+    m.set_clip_length(8)
+    assert m.state_dict()["video_model.video_model.t_former.pos_embedding"].shape == (1, 9, 512)
+    m.load_state_dict(O.make_state_dict(5, 8), strict=True)
+
+
+def test_constructor_signatures():
+    import inspect
+    sig = inspect.signature(A.TwoStreamAuralVisualFormer.__init__)
+    assert list(sig.parameters)[1:] == ["modality", "video_pretrained", "audio_pretrained", "task"]
+    assert sig.parameters["task"].default == "EX" and sig.parameters["modality"].default == "A;V;M"
+    assert list(inspect.signature(A.Transformer.__init__).parameters)[1:] == ["dim", "depth", "heads", "dim_head", "mlp_dim", "dropout"]
+    assert list(inspect.signature(A.TFormer.__init__).parameters)[1:] == ["num_patches", "dim", "depth", "heads", "mlp_dim", "dim_head", "dropout"]
+    assert list(inspect.signature(A.AU_former.__init__).parameters)[1:] == ["input_dim", "emb_dim", "dropout"]
+    assert list(inspect.signature(A.former_AU_head.__init__).parameters)[1:] == ["emb_dim", "dropout"]
+    assert A.tformer_AU_head is A.former_AU_head
+    vm = A.VideoModel()
+    vm.config_modality("A;V;M")
+    assert vm.num_channels == 4 and vm.s_former.conv1.in_channels == 4
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "multi-modal-multi-label-facial-action-unit-detection-with-transformer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read(), f"{f} mentions the oracle"
