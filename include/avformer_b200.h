@@ -72,6 +72,8 @@ typedef struct avf_stack_shape {
 /* ---- library / device ------------------------------------------------------------------- */
 int         avf_abi_version(void);
 const char* avf_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches evidence). */
+uint64_t    avf_launch_count(void);
 /* SM count, compute capability major*10+minor, and whether the tcgen05 path is usable. */
 int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05);
 

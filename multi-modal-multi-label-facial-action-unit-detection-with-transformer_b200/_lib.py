@@ -45,6 +45,7 @@ class StackShape(ctypes.Structure):
 SIGNATURES = {
     "avf_abi_version": (ctypes.c_int, []),
     "avf_last_error": (ctypes.c_char_p, []),
+    "avf_launch_count": (ctypes.c_uint64, []),
     "avf_device_info": (ctypes.c_int, [ctypes.POINTER(_i32)] * 3),
     "avf_encoder_workspace_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
     "avf_encoder_stack_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _i32,

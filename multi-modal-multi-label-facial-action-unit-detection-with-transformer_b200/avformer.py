@@ -117,6 +117,22 @@ class TwoStreamAuralVisualFormer(nn.Module):
             return torch.zeros(bs, 21, device=clip.device)
         return self.au_head.logits21_(fused, bs)
 
+    def hot_path(self, stage3, frame_feat, audio_feat, want_decisions=False):
+        """The transformer stack alone, on tensors already at its boundaries (what bench.py times and
+        what SURVEY.md §8 scopes): SFormer on stage-3 maps [B*T,256,7,7] (fp32/bf16), then TFormer on frame
+        features [B*T,512], the two AU_formers (video: TFormer cls rows; audio: audio_feat [B,512] fp32) and
+        the fusion head.  In the full model the conv stage 4 sits between SFormer and TFormer; here the two
+        are fed independently.  Returns (sformer_out, out21 [B,21]) (+ int32 decisions [B,12])."""
+        vm = self.video_model.video_model
+        s_out = vm.s_former.sformer(stage3)
+        tok, n_clips = vm.t_former.tokens(frame_feat)
+        fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=tok.device)
+        a_feat = audio_feat if (audio_feat.dtype == torch.float32 and audio_feat.is_contiguous()) else audio_feat.float().contiguous()
+        self.audio_model.au_head.tokens_into(a_feat, a_feat.shape[1], n_clips, out=fused, ld_out=256)
+        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        res = self.au_head.logits21_(fused, n_clips, want_decisions)
+        return (s_out,) + (res if want_decisions else (res,))
+
     # -- loss helpers (models/avformer.py:108-123) ------------------------------------------------
     def get_au_loss(self, y_pred, y_true):
         return self.loss_AU(y_pred[:, :12], y_true)

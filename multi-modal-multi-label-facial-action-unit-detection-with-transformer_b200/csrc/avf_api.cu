@@ -1,5 +1,6 @@
 // extern "C" surface of libavformer_b200.so (include/avformer_b200.h) and the host-side
 // orchestration of one encoder stack.  No torch types, no CPU compute path.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -10,6 +11,9 @@
 namespace avf {
 
 static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -134,6 +138,8 @@ extern "C" {
 int avf_abi_version(void) { return AVF_ABI_VERSION; }
 
 const char* avf_last_error(void) { return g_err; }
+
+uint64_t avf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05) {
   int e = require_device();

@@ -16,6 +16,7 @@ namespace avf {
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launch();   // bumps the counter avf_launch_count() reports
 
 #define AVF_REQUIRE(cond, code, ...)            \
   do {                                          \
@@ -33,6 +34,7 @@ int check_cuda(cudaError_t e, const char* what);
 
 #define AVF_LAUNCH_CHECK(name)                                \
   do {                                                        \
+    avf::count_launch();                                      \
     int _e = avf::check_cuda(cudaGetLastError(), name);       \
     if (_e != 0) return _e;                                   \
   } while (0)

@@ -1,0 +1,47 @@
+"""Data-parallel plumbing: clips are independent units, so ranks take contiguous shards of
+the batch, weights are replicated, and the only collectives are the logit gather in evaluation and the
+gradient all-reduce in training.  torch.distributed (NCCL on GPUs, gloo in CPU tests) is the transport."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of rank `rank`; the first n_items % world ranks take one extra item."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_batch(x: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Slice every tensor of a reference-style batch dict (train.py:207-218) along dim 0."""
+    n = next(iter(x.values())).shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    return {k: v[lo:hi] for k, v in x.items()}
+
+
+def gather_logits(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather per-rank [b_r, 21] outputs into the full [n_total, 21] batch (ragged shards allowed)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(n_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group) if local.is_cuda else dist.all_gather(list(out.chunk(world)), pad, group=group)
+    return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum-all-reduce a flat gradient bucket and divide by the world size (equal valid-row counts per rank
+    make this the global AULoss gradient, SURVEY.md §8e caveat 2)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.div_(dist.get_world_size(group))
+    return flat_grad
