@@ -28,12 +28,59 @@ struct GemmCfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 128 + 1024;   // barriers + slack for 1024B alignment
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;       // power of two >= 32
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+  static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator; power of two >= 32
 };
 
+// Epilogue math on one 32-column chunk held in registers, then the store of that chunk.
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
+                                               const float* __restrict__ bias, const float* res, int ld_res, int flags) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (flags & AVF_EPI_BIAS) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+      f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if (flags & AVF_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_tanh<true>(f[j]);
+  }
+  if (flags & AVF_EPI_RESIDUAL) {
+    const float* rp = res + size_t(row) * ld_res + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 r = *reinterpret_cast<const float4*>(rp + j);
+      f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+    }
+  }
+  OutT* cp = C + size_t(row) * ldc + col0;
+  if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(cp) + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o;
+      o.x = pack_bf16x2(f[j], f[j + 1]);
+      o.y = pack_bf16x2(f[j + 2], f[j + 3]);
+      o.z = pack_bf16x2(f[j + 4], f[j + 5]);
+      o.w = pack_bf16x2(f[j + 6], f[j + 7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp) + j) = o;
+    }
+  }
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// (n-block fastest, so CTAs that run concurrently share the A tile in L2).  The TMEM accumulator is double
+// buffered (2 x BN columns): the MMA warp fills buffer (t+1)&1 while the 8 epilogue warps drain buffer t&1.
 template <int BN, int STAGES, typename OutT>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(384, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  OutT* C, int ldc, const float* __restrict__ bias,
                  const float* res, int ld_res, int M, int N, int K, int flags) {
@@ -42,12 +89,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;       // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kblocks = K / BK;
+  const int n_blocks = N / BN;
+  const int n_tiles = n_blocks * ((M + BM - 1) / BM);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -56,10 +105,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);               // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -70,93 +122,77 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
-        tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
+          tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t da = make_desc_sw128_kmajor(a_addr);
-        const uint64_t db = make_desc_sw128_kmajor(a_addr + Cfg::A_BYTES);
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128_kmajor(a_addr);
+          const uint64_t db = make_desc_sw128_kmajor(a_addr + Cfg::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance along K inside the 128B swizzle span: +32 bytes per UMMA_K (>>4 in descriptor units)
-          umma_bf16(tmem_base, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance along K inside the 128B swizzle span: +32 bytes per UMMA_K (>>4 in descriptor units)
+            umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
+        umma_commit(&acc_full[buf]);              // accumulator complete
       }
-      umma_commit(accum_bar);                // accumulator complete
     }
-  } else {
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const bool has_bias = flags & AVF_EPI_BIAS, has_gelu = flags & AVF_EPI_GELU, has_res = flags & AVF_EPI_RESIDUAL;
+  } else if (warp >= 4) {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;             // which half of the tile's columns
+    constexpr int HALF_COLS = BN / 2;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * BN + half * HALF_COLS;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
-      tmem_ld_wait();
-      if (row < M) {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (has_bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-          }
+      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + uint32_t(c0), v);
+        tmem_ld_wait();
+        if (c0 + 32 >= HALF_COLS) {               // last chunk is in registers: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (has_gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_tanh<true>(f[j]);
-        }
-        if (has_res) {
-          const float* rp = res + size_t(row) * ld_res + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 r = *reinterpret_cast<const float4*>(rp + j);
-            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-          }
-        }
-        OutT* cp = C + size_t(row) * ldc + n0 + c0;
-        if constexpr (sizeof(OutT) == 4) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(cp) + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(f[j], f[j + 1]);
-            o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-            o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-            o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp) + j) = o;
-          }
-        }
+        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, C, ldc, bias, res, ld_res, flags);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -199,18 +235,32 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
   return 0;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES, typename OutT>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, OutT* c, int ldc, const float* bias,
+static int launch_gemm(const void* a, int lda, const void* w, OutT* c, int ldc, const float* bias,
                        const float* res, int ld_res, int m, int n, int k, int flags, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, STAGES>;
+  CUtensorMap ta, tw;
+  int e = make_tmap_bf16_2d(&ta, a, m, k, lda, BM);
+  if (e) return e;
+  e = make_tmap_bf16_2d(&tw, w, n, k, k, BN);
+  if (e) return e;
   auto kern = gemm_umma_kernel<BN, STAGES, OutT>;
   static bool configured = false;
   if (!configured) {
     AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(n / BN, ceil_div(m, BM));
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags);
+  const int n_tiles = (n / BN) * ceil_div(m, BM);
+  kern<<<min(n_tiles, sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags);
   AVF_LAUNCH_CHECK("gemm_umma_kernel");
   return 0;
 }
@@ -223,20 +273,23 @@ int linear_umma(const void* a, int lda, const void* w, const float* bias, const 
   AVF_REQUIRE(n % 64 == 0, AVF_EUNSUPPORTED, "linear(bf16): N=%d must be a multiple of 64", n);
   AVF_REQUIRE(ldc % 8 == 0 && (!(flags & AVF_EPI_RESIDUAL) || ld_res % 4 == 0), AVF_EINVAL,
               "linear(bf16): ldc=%d / ld_res=%d break vector alignment", ldc, ld_res);
-  const int bn = (n % 128 == 0) ? 128 : 64;
-  CUtensorMap ta, tw;
-  int e = make_tmap_bf16_2d(&ta, a, m, k, lda, BM);
-  if (e) return e;
-  e = make_tmap_bf16_2d(&tw, w, n, k, k, bn);
-  if (e) return e;
-  if (bn == 128) {
-    if (c_mode == AVF_BF16)
-      return launch_gemm<128, 3, __nv_bfloat16>(ta, tw, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);
-    return launch_gemm<128, 3, float>(ta, tw, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);
+  // widest tile that still gives every SM at least two tiles; small problems get narrower tiles for parallelism
+  const int m_tiles = ceil_div(m, BM), sms = sm_count();
+  int bn = 64;
+  if (n % 256 == 0 && m_tiles * (n / 256) >= 2 * sms) bn = 256;
+  else if (n % 128 == 0 && m_tiles * (n / 128) >= sms) bn = 128;
+  else if (n % 128 == 0 && n / 128 * m_tiles >= sms / 2 && n >= 512) bn = 128;
+#define AVF_GEMM(BN_, ST_)                                                                                                         \
+  if (bn == BN_) {                                                                                                                 \
+    if (c_mode == AVF_BF16)                                                                                                        \
+      return launch_gemm<BN_, ST_, __nv_bfloat16>(a, lda, w, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream); \
+    return launch_gemm<BN_, ST_, float>(a, lda, w, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);          \
   }
-  if (c_mode == AVF_BF16)
-    return launch_gemm<64, 4, __nv_bfloat16>(ta, tw, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);
-  return launch_gemm<64, 4, float>(ta, tw, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);
+  AVF_GEMM(256, 4)
+  AVF_GEMM(128, 6)
+  AVF_GEMM(64, 8)
+#undef AVF_GEMM
+  return AVF_EUNSUPPORTED;
 }
 
 }  // namespace avf

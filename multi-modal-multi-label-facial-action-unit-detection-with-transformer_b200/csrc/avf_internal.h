@@ -24,6 +24,9 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
                int c_mode, int m, int n, int k, int flags, cudaStream_t st);
 int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
+// avf_attention_mma.cu
+int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+
 // avf_gemm_umma.cu
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
                 int c_mode, int m, int n, int k, int flags, cudaStream_t st);

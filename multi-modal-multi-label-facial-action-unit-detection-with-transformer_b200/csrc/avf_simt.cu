@@ -2,6 +2,7 @@
 // true fp32 products, which the tensor cores do not offer) and the small-sequence attention
 // (N <= 64 tokens: 12 / 17 / 49) used by both modes outside the fused tcgen05 layer kernel.
 #include "avf_common.cuh"
+#include "avf_internal.h"
 
 namespace avf {
 
@@ -200,10 +201,7 @@ static int launch_attention(const void* qkv, void* out, int n_seq, int n_tok, in
 int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st) {
   AVF_REQUIRE(n_seq > 0 && n_tok > 0 && heads > 0, AVF_EINVAL, "attention: n_seq=%d n_tok=%d heads=%d", n_seq, n_tok, heads);
   AVF_REQUIRE(dim_head == 32 || dim_head == 64, AVF_EUNSUPPORTED, "attention: dim_head=%d (supported: 32, 64)", dim_head);
-  if (io_mode == AVF_BF16) {
-    return dim_head == 32 ? launch_attention<__nv_bfloat16, 32>(qkv, out, n_seq, n_tok, heads, st)
-                          : launch_attention<__nv_bfloat16, 64>(qkv, out, n_seq, n_tok, heads, st);
-  }
+  if (io_mode == AVF_BF16) return attention_mma_bf16(qkv, out, n_seq, n_tok, heads, dim_head, st);   // tensor cores
   return dim_head == 32 ? launch_attention<float, 32>(qkv, out, n_seq, n_tok, heads, st)
                         : launch_attention<float, 64>(qkv, out, n_seq, n_tok, heads, st);
 }

@@ -101,26 +101,33 @@ def fam_gemm():
         print(f"gemm_umma {m}x{n}x{k} bias+res:", _err(c, ref + b.double() + r.double()))
         c = AF.linear_fwd(a, w, b, gelu=True, out_dtype=torch.bfloat16, precision="bf16")
         print(f"gemm_umma {m}x{n}x{k} bias+gelu bf16out:", _err(c.float(), torch.nn.functional.gelu(ref + b.double(), approximate="tanh")))
-    # timing of a TFormer-sized GEMM
-    a = torch.randn(8704, 512, device="cuda").bfloat16()
-    w = torch.randn(1536, 512, device="cuda").bfloat16()
-    for _ in range(3):
-        AF.linear_fwd(a, w, out_dtype=torch.bfloat16, precision="bf16")
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(20):
-        AF.linear_fwd(a, w, out_dtype=torch.bfloat16, precision="bf16")
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print(f"gemm_umma 8704x1536x512: {ms * 1e3:.1f} us  {2 * 8704 * 1536 * 512 / ms / 1e9:.1f} TFLOP/s")
-    e0.record()
-    for _ in range(20):
-        torch.matmul(a, w.t())
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print(f"cublas    8704x1536x512: {ms * 1e3:.1f} us  {2 * 8704 * 1536 * 512 / ms / 1e9:.1f} TFLOP/s")
+    # timings (CUDA events, 10 launches after 2 warm-ups)
+    def timeit(fn, reps=10):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    for (m, n, k, od, gelu, res) in ((8704, 1536, 512, torch.bfloat16, False, False), (8704, 512, 512, torch.float32, False, True),
+                                     (8704, 1024, 512, torch.bfloat16, True, False), (8704, 512, 1024, torch.float32, False, True),
+                                     (401408, 768, 256, torch.bfloat16, False, False), (401408, 256, 256, torch.float32, False, True),
+                                     (401408, 512, 256, torch.bfloat16, True, False), (401408, 256, 512, torch.float32, False, True),
+                                     (6144, 768, 128, torch.bfloat16, False, False), (6144, 128, 256, torch.float32, False, True)):
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        w = torch.randn(n, k, device="cuda").bfloat16()
+        b = torch.randn(n, device="cuda")
+        r = torch.randn(m, n, device="cuda") if res else None
+        ms = timeit(lambda: AF.linear_fwd(a, w, b, r, gelu=gelu, out_dtype=od, precision="bf16"))
+        ms2 = timeit(lambda: torch.matmul(a, w.t()))
+        print(f"gemm_umma {m}x{n}x{k} out={str(od)[6:]} gelu={gelu} res={res}: {ms * 1e3:8.1f} us {2 * m * n * k / ms / 1e9:7.1f} TFLOP/s | cuBLAS plain: {ms2 * 1e3:8.1f} us")
+    for (ns, nt, h, dh) in ((8192, 49, 8, 32), (512, 17, 8, 64), (512, 12, 8, 32)):
+        qkv = torch.randn(ns * nt, 3 * h * dh, device="cuda").bfloat16()
+        ms = timeit(lambda: AF.attention_fwd(qkv, ns, nt, h, dh))
+        print(f"attention_mma seq={ns} tok={nt} dh={dh}: {ms * 1e3:8.1f} us  {4 * ns * h * nt * nt * dh / ms / 1e9:7.1f} TFLOP/s")
 
 
 def fam_attention():
