@@ -77,6 +77,12 @@ uint64_t    avf_launch_count(void);
 /* SM count, compute capability major*10+minor, and whether the tcgen05 path is usable. */
 int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05);
 
+/* The encoder stacks with dim 256 / 8 heads x 32 (SFormer, fusion head) run as ONE persistent tcgen05 kernel per
+ * stack in mode AVF_BF16 (residual stream in TMEM, see csrc/avf_layer_fused.cu).  avf_set_fused_enabled(0) forces the
+ * kernel-per-operation path instead (used by the A/B parity tests); returns the previous setting. */
+int         avf_set_fused_enabled(int enabled);
+int         avf_encoder_fused_supported(const avf_stack_shape* s, int mode);
+
 /* ---- workspace ---------------------------------------------------------------------------- */
 /* Bytes of scratch avf_encoder_stack_fwd needs for this shape/mode (replaces the implicit ATen
  * temporaries of models/heads.py:219-239). */

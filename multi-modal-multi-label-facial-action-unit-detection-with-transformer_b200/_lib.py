@@ -47,6 +47,8 @@ SIGNATURES = {
     "avf_last_error": (ctypes.c_char_p, []),
     "avf_launch_count": (ctypes.c_uint64, []),
     "avf_device_info": (ctypes.c_int, [ctypes.POINTER(_i32)] * 3),
+    "avf_set_fused_enabled": (ctypes.c_int, [ctypes.c_int]),
+    "avf_encoder_fused_supported": (ctypes.c_int, [ctypes.POINTER(StackShape), ctypes.c_int]),
     "avf_encoder_workspace_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
     "avf_encoder_stack_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _i32,
                                              _c_p, _i32, _c_p, _sz, _c_p]),

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "../../include/avformer_b200.h"
+
 namespace avf {
 
 // avf_rowops.cu
@@ -26,6 +28,11 @@ int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_to
 
 // avf_attention_mma.cu
 int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+
+// avf_layer_fused.cu: whole encoder stack in one persistent tcgen05 kernel (dim 256, 8 heads x 32)
+bool encoder_fused_supported(const avf_stack_shape* s);
+int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
+                  const float* pos, cudaStream_t st);
 
 // avf_gemm_umma.cu
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,

@@ -252,3 +252,12 @@ def device_info() -> Dict[str, int]:
     a, b, c = _lib._i32(), _lib._i32(), _lib._i32()
     check(_lib.lib().avf_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "device_info")
     return {"sm_count": a.value, "cc": b.value, "has_tcgen05": c.value}
+
+
+def set_fused_enabled(enabled: bool) -> bool:
+    """Toggle the one-kernel-per-stack tcgen05 path (dim 256 / 8x32 stacks); returns the previous setting."""
+    return bool(_lib.lib().avf_set_fused_enabled(1 if enabled else 0))
+
+
+def encoder_fused_supported(shape: StackShape, precision="bf16") -> bool:
+    return bool(_lib.lib().avf_encoder_fused_supported(ctypes.byref(shape), _mode(precision)))
