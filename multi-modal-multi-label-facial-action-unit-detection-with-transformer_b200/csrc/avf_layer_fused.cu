@@ -120,60 +120,73 @@ struct Worker {
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[bar]);
   }
-  __device__ __forceinline__ void load_x(float (&v)[128]) {     // this thread's half row of the residual stream
+  // Statistics are accumulated on chunks as shifted sums (shift = the thread's first element) and merged with the
+  // partner thread by Chan's formula, so one sweep over the row is enough and nothing cancels catastrophically.
+  struct Stats {
+    float shift, s, ss;
+    bool have;
+    __device__ __forceinline__ void add(const float (&x)[32]) {
+      if (!have) {
+        shift = x[0];
+        have = true;
+      }
 #pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = x[j] - shift;
+        s += d;
+        ss = fmaf(d, d, ss);
+      }
+    }
+  };
+  __device__ __forceinline__ void finish_stats(const Stats& st, float& mean, float& rstd) {
+    const float mean_g = st.shift + st.s * (1.f / 128.f);
+    const float m2_g = fmaxf(st.ss - st.s * st.s * (1.f / 128.f), 0.f);
+    const float mean_o = exchange(mean_g), m2_o = exchange(m2_g);
+    const float dm = mean_g - mean_o;
+    mean = 0.5f * (mean_g + mean_o);
+    rstd = rsqrtf((m2_g + m2_o + dm * dm * 64.f) * (1.f / DIM) + 1e-5f);
+  }
+  // Sweep 1 of a LayerNorm whose input already sits in TMEM (x1 after the out-projection, x2 after the MLP).
+  __device__ __forceinline__ void stats_from_tmem(float& mean, float& rstd) {
+    Stats st{0.f, 0.f, 0.f, false};
+#pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tl + TM_X + g * 128 + c0, r);
+      float x[32];
+      tmem_ld32(tl + TM_X + g * 128 + c0, reinterpret_cast<uint32_t(&)[32]>(x));
+      tmem_ld_wait();
+      st.add(x);
+    }
+    finish_stats(st, mean, rstd);
+  }
+  // Sweep 2: LN(x) -> A0 (bf16, K-major SW128 panels), x + next_bias -> TMEM; then signal the MMA thread.
+  __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ next_bias) {
+    const int cbase = g * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float x[32];
+      tmem_ld32(tl + TM_X + cbase + c0, reinterpret_cast<uint32_t(&)[32]>(x));
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[c0 + j] = __uint_as_float(r[j]);
-    }
-  }
-  // LayerNorm of the row (two threads), x + next_bias -> TMEM, LN(x) -> A0 (bf16, K-major SW128 panels)
-  __device__ __forceinline__ void ln_phase(float (&v)[128], const float* __restrict__ gamma, const float* __restrict__ beta,
-                                           const float* __restrict__ next_bias, bool full_barrier) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 128; ++j) s += v[j];
-    s += exchange(s);
-    const float mean = s * (1.f / DIM);
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 128; ++j) {
-      const float d = v[j] - mean;
-      sq = fmaf(d, d, sq);
-    }
-    sq += exchange(sq);
-    const float rstd = rsqrtf(sq * (1.f / DIM) + 1e-5f);
-    if (full_barrier) bar_sync(5, 256);      // every worker has read its part of the staged input out of A0
-    const int cbase = g * 128;
-#pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-      const int col = cbase + ch * 8;
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-      const float* x = &v[ch * 8];
-      uint4 pk;
-      pk.x = pack_bf16x2(fmaf((x[0] - mean) * rstd, g0.x, b0.x), fmaf((x[1] - mean) * rstd, g0.y, b0.y));
-      pk.y = pack_bf16x2(fmaf((x[2] - mean) * rstd, g0.z, b0.z), fmaf((x[3] - mean) * rstd, g0.w, b0.w));
-      pk.z = pack_bf16x2(fmaf((x[4] - mean) * rstd, g1.x, b1.x), fmaf((x[5] - mean) * rstd, g1.y, b1.y));
-      pk.w = pack_bf16x2(fmaf((x[6] - mean) * rstd, g1.z, b1.z), fmaf((x[7] - mean) * rstd, g1.w, b1.w));
-      const int panel = col >> 6, chunk = (col & 63) >> 3;
-      *reinterpret_cast<uint4*>(smem + OFF_A0 + panel * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
-    }
-#pragma unroll
-    for (int c0 = 0; c0 < 128; c0 += 8) {
-      uint32_t r[8];
-#pragma unroll
-      for (int j = 0; j < 8; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(next_bias + cbase + c0 + j));
-        r[j] = __float_as_uint(v[c0 + j] + b.x);
-        r[j + 1] = __float_as_uint(v[c0 + j + 1] + b.y);
-        r[j + 2] = __float_as_uint(v[c0 + j + 2] + b.z);
-        r[j + 3] = __float_as_uint(v[c0 + j + 3] + b.w);
+      for (int ch = 0; ch < 4; ++ch) {
+        const int col = cbase + c0 + ch * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+        const float* y = &x[ch * 8];
+        uint4 pk;
+        pk.x = pack_bf16x2(fmaf((y[0] - mean) * rstd, g0.x, b0.x), fmaf((y[1] - mean) * rstd, g0.y, b0.y));
+        pk.y = pack_bf16x2(fmaf((y[2] - mean) * rstd, g0.z, b0.z), fmaf((y[3] - mean) * rstd, g0.w, b0.w));
+        pk.z = pack_bf16x2(fmaf((y[4] - mean) * rstd, g1.x, b1.x), fmaf((y[5] - mean) * rstd, g1.y, b1.y));
+        pk.w = pack_bf16x2(fmaf((y[6] - mean) * rstd, g1.z, b1.z), fmaf((y[7] - mean) * rstd, g1.w, b1.w));
+        const int panel = col >> 6, chunk = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(smem + OFF_A0 + panel * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
       }
-      tmem_st8(tl + TM_X + cbase + c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(next_bias + cbase + c0 + j));
+        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+      }
+      tmem_st32(tl + TM_X + cbase + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
     }
     tmem_st_wait();
     arrive(B_A0_READY);
@@ -213,51 +226,52 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
     const int seqs_here = min(spt, a.n_seq - tile * spt);
     const int rows_here = seqs_here * n_tok;
     const size_t grow = size_t(tile) * spt * n_tok + row;           // global token row (IO_ROWS_F32)
-    float v[128];
-    // ---- tile input -------------------------------------------------------------------------
-    if constexpr (IO == IO_NCHW_BF16) {
-      mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
-      if (row < rows_here) {
-        const int fr = row / n_tok;
-        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
-        const float* pp = a.pos + t_in_seq * DIM + g * 128;
+    // ---- tile input: x (+ pos) -> TMEM, statistics of LN1 on the way --------------------------------------
+    float mean, rstd;
+    {
+      Worker::Stats st{0.f, 0.f, 0.f, false};
+      const bool valid = row < rows_here;
+      if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
+      const int fr = row / n_tok;
+      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
+      const float* src32 = static_cast<const float*>(a.in) + grow * a.ld_in + g * 128;
+      const float* pp = a.pos + t_in_seq * DIM + g * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float x[32];
+        if (valid) {
+          if constexpr (IO == IO_NCHW_BF16) {
 #pragma unroll
-        for (int j = 0; j < 128; j += 4) {
-          const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j));
-          v[j] = __bfloat162float(src[(j + 0) * n_tok]) + p4.x;
-          v[j + 1] = __bfloat162float(src[(j + 1) * n_tok]) + p4.y;
-          v[j + 2] = __bfloat162float(src[(j + 2) * n_tok]) + p4.z;
-          v[j + 3] = __bfloat162float(src[(j + 3) * n_tok]) + p4.w;
-        }
-      } else {
+            for (int j = 0; j < 32; ++j) x[j] = __bfloat162float(src16[(c0 + j) * n_tok]);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 128; ++j) v[j] = 0.f;
-      }
-    } else {
-      if (row < rows_here) {
-        const float* src = static_cast<const float*>(a.in) + grow * a.ld_in + g * 128;
-#pragma unroll
-        for (int j = 0; j < 128; j += 4) {
-          const float4 x4 = *reinterpret_cast<const float4*>(src + j);
-          v[j] = x4.x; v[j + 1] = x4.y; v[j + 2] = x4.z; v[j + 3] = x4.w;
-        }
-        if (a.pos != nullptr) {
-          const float* pp = a.pos + t_in_seq * DIM + g * 128;
-#pragma unroll
-          for (int j = 0; j < 128; j += 4) {
-            const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + j));
-            v[j] += p4.x; v[j + 1] += p4.y; v[j + 2] += p4.z; v[j + 3] += p4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 x4 = *reinterpret_cast<const float4*>(src32 + c0 + j);
+              x[j] = x4.x; x[j + 1] = x4.y; x[j + 2] = x4.z; x[j + 3] = x4.w;
+            }
           }
-        }
-      } else {
+          if (a.pos != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 128; ++j) v[j] = 0.f;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + c0 + j));
+              x[j] += p4.x; x[j + 1] += p4.y; x[j + 2] += p4.z; x[j + 3] += p4.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.f;
+        }
+        st.add(x);
+        tmem_st32(tl + TM_X + g * 128 + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
       }
+      tmem_st_wait();
+      w.finish_stats(st, mean, rstd);
+      if constexpr (IO == IO_NCHW_BF16) bar_sync(5, 256);   // every worker has read its part of the staged frames out of A0
     }
 
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      w.ln_phase(v, L.ln1_g, L.ln1_b, L.b_out, IO == IO_NCHW_BF16 && l == 0);
+      w.normalize_from_tmem(mean, rstd, L.ln1_g, L.ln1_b, L.b_out);
 
       // ---- attention: per head  E1 (QKV -> smem), E3 of the previous head (O -> A1), E2 (softmax) -------------
       float inv_l = 0.f;
@@ -385,8 +399,8 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       // ---- LN2 on x1 = x + attention (accumulated in TMEM by the out-projection) ------------------------------
       mbar_wait(&bars[B_X1_FULL], (n_x1++) & 1);
       tc_fence_after();
-      w.load_x(v);
-      w.ln_phase(v, L.ln2_g, L.ln2_b, L.b_ff2, false);
+      w.stats_from_tmem(mean, rstd);
+      w.normalize_from_tmem(mean, rstd, L.ln2_g, L.ln2_b, L.b_ff2);
 
       // ---- MLP: per 128-column chunk of the hidden layer, bias + tanh-GELU -> bf16 A operand ---------------------
 #pragma unroll 1
@@ -419,29 +433,38 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       // ---- x2 = x1 + MLP, accumulated in TMEM by the second MLP GEMM --------------------------------------------
       mbar_wait(&bars[B_X2_FULL], (n_x2++) & 1);
       tc_fence_after();
-      w.load_x(v);
+      if (l + 1 < a.depth) w.stats_from_tmem(mean, rstd);
     }
 
     // ---- tile output ----------------------------------------------------------------------------
-    if constexpr (IO == IO_NCHW_BF16) {
-      if (row < rows_here) {
-        const int fr = row / n_tok;
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(smem + OFF_A1) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
+    {
+      const bool valid = row < rows_here;
+      const int fr = row / n_tok;
+      __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(smem + OFF_A1) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
+      float* dst32 = static_cast<float*>(a.out) + grow * a.ld_out + g * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float x[32];
+        tmem_ld32(tl + TM_X + g * 128 + c0, reinterpret_cast<uint32_t(&)[32]>(x));
+        tmem_ld_wait();
+        if (valid) {
+          if constexpr (IO == IO_NCHW_BF16) {
 #pragma unroll
-        for (int j = 0; j < 128; ++j) dst[j * n_tok] = __float2bfloat16_rn(v[j]);
-      }
-      fence_proxy_async_smem();
-      bar_sync(5, 256);
-      if (threadIdx.x == WORKER_T0) {
-        __nv_bfloat16* gdst = static_cast<__nv_bfloat16*>(a.out) + size_t(tile) * spt * n_tok * DIM;
-        bulk_store_1d(gdst, smem + OFF_A1, uint32_t(rows_here) * DIM * 2);
-        bulk_wait_read0();       // A1 is written again by this tile's successor (ordered by the bar_sync in its ln_phase)
-      }
-    } else {
-      if (row < rows_here) {
-        float* dst = static_cast<float*>(a.out) + grow * a.ld_out + g * 128;
+            for (int j = 0; j < 32; ++j) dst16[(c0 + j) * n_tok] = __float2bfloat16_rn(x[j]);
+          } else {
 #pragma unroll
-        for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst32 + c0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          }
+        }
+      }
+      if constexpr (IO == IO_NCHW_BF16) {
+        fence_proxy_async_smem();
+        bar_sync(5, 256);
+        if (threadIdx.x == WORKER_T0) {
+          __nv_bfloat16* gdst = static_cast<__nv_bfloat16*>(a.out) + size_t(tile) * spt * n_tok * DIM;
+          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(rows_here) * DIM * 2);
+          bulk_wait_read0();     // A1 is written again by the next tile's attention (ordered by the bar_sync after its input sweep)
+        }
       }
     }
   }
