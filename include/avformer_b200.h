@@ -82,6 +82,9 @@ int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05
  * kernel-per-operation path instead (used by the A/B parity tests); returns the previous setting. */
 int         avf_set_fused_enabled(int enabled);
 int         avf_encoder_fused_supported(const avf_stack_shape* s, int mode);
+/* Developer aid: 64 per-phase cycle counters of the fused kernel when the library is built with -DAVF_FUSED_PROF
+ * (tools/fused_phases.py); AVF_EUNSUPPORTED otherwise. */
+int         avf_debug_fused_prof(uint64_t* out64, int reset);
 
 /* ---- workspace ---------------------------------------------------------------------------- */
 /* Bytes of scratch avf_encoder_stack_fwd needs for this shape/mode (replaces the implicit ATen

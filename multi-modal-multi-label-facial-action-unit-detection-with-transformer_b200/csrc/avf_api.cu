@@ -153,6 +153,9 @@ int avf_encoder_fused_supported(const avf_stack_shape* s, int mode) {
   return (s != nullptr && mode == AVF_BF16 && s->n_seq > 0 && encoder_fused_supported(s)) ? 1 : 0;
 }
 
+/* Debug: per-phase cycle counters of the fused encoder kernel (library built with -DAVF_FUSED_PROF); else AVF_EUNSUPPORTED. */
+int avf_debug_fused_prof(uint64_t* out64, int reset) { return fused_prof_read(reinterpret_cast<unsigned long long*>(out64), reset); }
+
 int avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05) {
   int e = require_device();
   if (e) return e;

@@ -31,6 +31,7 @@ int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int hea
 
 // avf_layer_fused.cu: whole encoder stack in one persistent tcgen05 kernel (dim 256, 8 heads x 32)
 bool encoder_fused_supported(const avf_stack_shape* s);
+int fused_prof_read(unsigned long long* out64, int reset);   // phase counters, only with -DAVF_FUSED_PROF
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, cudaStream_t st);
 

@@ -10,11 +10,11 @@
 //   * attention is per head on the tensor cores: [Q|K|V]_h = LN(x) Wqkv_h^T (N=96), S = Q K^T over the whole tile
 //     (block-diagonal: a row only uses the columns of its own sequence), softmax in registers, P written back as
 //     bf16 INTO the S columns of TMEM and used as the A operand of O = P V (V is an MN-major B operand);
-//   * weights are streamed from L2 by TMA through a 4-slot ring, activations enter / leave as whole NCHW frames
+//   * weights are streamed from L2 by TMA through a 3-slot ring, activations enter / leave as whole NCHW frames
 //     by bulk copies (SFormer, models/vformer.py:245-259) or as fp32 rows.
 //
 // Warp roles: 0 = TMA producer (weights; also the next tile's input frames), 1 = TMEM allocator + MMA issuer (one thread),
-// 2..9 = row workers (warp w owns TMEM lanes 32*(w%4)..+31; warps 2-5 / 6-9 split the columns).  320 threads -> 200 registers each.
+// 2..17 = row workers (warp w owns TMEM lanes 32*(w%4)..+31; four warps share a lane quarter and split the columns).
 #include <cuda.h>
 
 #include "avf_common.cuh"
@@ -27,10 +27,16 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 namespace {
 
 constexpr int DIM = 256, HEADS = 8, DH = 32;
-constexpr int MAX_DEPTH = 3;
-constexpr int NUM_THREADS = 320;
-constexpr int WORKER_T0 = 64;          // first worker thread
-constexpr int RING = 4, SLOT_BYTES = 16384;
+constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
+#ifndef AVF_FUSED_NSPLIT
+#define AVF_FUSED_NSPLIT 2
+#endif
+constexpr int NSPLIT = AVF_FUSED_NSPLIT;   // threads per token row (each owns DIM / NSPLIT columns of the residual stream)
+static_assert(NSPLIT == 2 || NSPLIT == 4, "NSPLIT");
+constexpr int WORKER_T0 = 64;              // first worker thread
+constexpr int NUM_WORKERS = 128 * NSPLIT;
+constexpr int NUM_THREADS = WORKER_T0 + NUM_WORKERS;
+constexpr int RING = 3, SLOT_BYTES = 16384;
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int OFF_A0 = 0;                          // 64 KB  LN output [128 x 256] bf16, 4 K-panels; also the NCHW input staging
@@ -38,21 +44,52 @@ constexpr int OFF_A1 = 65536;                      // 64 KB  attention output / 
 constexpr int OFF_Q = 131072;                      // 8 KB   Q_h [128 x 32] K-major SW64
 constexpr int OFF_K = OFF_Q + 8192;                // 8 KB   K_h
 constexpr int OFF_V = OFF_K + 8192;                // 2x8 KB V_h [128 tok x 32] MN-major SW64, double buffered
-constexpr int OFF_RING = OFF_V + 16384;            // 4 x 16 KB weight ring
-constexpr int OFF_XCH = OFF_RING + RING * SLOT_BYTES;   // 2 KB  row-pair exchange [2][128][2] floats
-constexpr int OFF_BAR = OFF_XCH + 2048;
-constexpr int SMEM_USED = OFF_BAR + 256;           // 231,680
-constexpr int SMEM_ALLOC = 232448;                 // 227 KB: everything the SM has
+constexpr int OFF_RING = OFF_V + 16384;            // 3 x 16 KB weight ring
+constexpr int OFF_XCH = OFF_RING + RING * SLOT_BYTES;   // row exchange [2][128][4] floats
+constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors (LN affine, biases), fp32
+constexpr int V_LN1G = 0, V_LN1B = 256, V_BOUT = 512, V_LN2G = 768, V_LN2B = 1024, V_BFF2 = 1280, V_BFF1 = 1536;
+constexpr int OFF_BAR = OFF_VEC + (V_BFF1 + MAX_MLP) * 4;
+constexpr int SMEM_USED = OFF_BAR + 256;
+constexpr int SMEM_ALLOC = SMEM_USED + 1024;       // slack for the 1024-byte alignment of the base
+static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 
 // TMEM columns
 constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, TM_H1 = 384;
 
 enum {
-  B_RING_FULL = 0, B_RING_EMPTY = 4, B_X0_FULL = 8, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
+  B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
   B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_HBUF_FREE, B_HBUF_FREE1, B_X2_FULL, NUM_BARS
 };
+static_assert(NUM_BARS * 8 + 8 <= 256, "barrier block");
 
 enum { IO_NCHW_BF16 = 0, IO_ROWS_F32 = 1 };
+
+// Optional phase timing (-DAVF_FUSED_PROF): CTA 0's MMA thread and first worker thread accumulate clock64() deltas per phase.
+#ifdef AVF_FUSED_PROF
+__device__ unsigned long long g_prof[64];
+struct Prof {
+  long long t0;
+  bool on;
+  __device__ __forceinline__ void start(bool enable) { on = enable; t0 = clock64(); }
+  __device__ __forceinline__ void mark(int idx) {
+    if (on) {
+      const long long t1 = clock64();
+      g_prof[idx] += (unsigned long long)(t1 - t0);
+      t0 = t1;
+    }
+  }
+};
+#else
+struct Prof {
+  __device__ __forceinline__ void start(bool) {}
+  __device__ __forceinline__ void mark(int) {}
+};
+#endif
+// worker phases
+enum { PW_INPUT = 0, PW_VEC, PW_LN1, PW_WAIT_D1, PW_E1, PW_WAIT_O, PW_E3, PW_WAIT_S, PW_E2, PW_WAIT_X1, PW_LN2, PW_WAIT_HACC, PW_GELU, PW_WAIT_X2,
+       PW_OUTPUT, PW_TILES,
+       // MMA thread phases
+       PM_WAIT_A0 = 32, PM_QKV, PM_WAIT_STAGED, PM_S, PM_WAIT_P, PM_PV, PM_WAIT_OD7, PM_OUT, PM_WAIT_A0B, PM_FF1, PM_WAIT_H, PM_FF2, PM_RINGWAIT };
 
 struct LayerArgs {
   CUtensorMap tm_qkv, tm_out, tm_w1, tm_w2;
@@ -60,13 +97,16 @@ struct LayerArgs {
   uint64_t pad_;
 };
 
+// A tile is 128 token rows = `spt` sequences, each padded to a row slot of `slot` rows (the power of two >= n_tok,
+// at least 16): row r belongs to sequence r / slot, token r % slot.  With slot >= 32 all rows of a warp belong to ONE
+// sequence, so the whole warp reads the same window of score columns.
 struct FusedArgs {
   LayerArgs layer[MAX_DEPTH];
   const void* in;
   void* out;
   const float* pos;          // [n_tok, 256] or nullptr
   int ld_in, ld_out;         // IO_ROWS_F32 row strides (elements)
-  int n_seq, n_tok, spt, n_tiles, n_chunks, depth;
+  int n_seq, n_tok, slot, slot_log2, spt, n_tiles, n_chunks, depth;
 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -75,15 +115,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// tanh-GELU (models/heads.py:164-166) as 0.5x(1+tanh(x(c0 + c1 x^2))): 6 instructions per element
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = x * fmaf(x * x, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, fast_tanh(u), hx);
+}
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
                : "memory");
 }
 __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
@@ -97,22 +152,55 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 
 __device__ __forceinline__ uint64_t desc_sw64(uint32_t addr) { return make_desc(addr, 16, 512, 4); }
 
+__device__ __forceinline__ uint4 pack8(const float* x) {
+  uint4 pk;
+  pk.x = pack_bf16x2(x[0], x[1]);
+  pk.y = pack_bf16x2(x[2], x[3]);
+  pk.z = pack_bf16x2(x[4], x[5]);
+  pk.w = pack_bf16x2(x[6], x[7]);
+  return pk;
+}
+__device__ __forceinline__ uint4 pack8u(const uint32_t* r) {
+  uint4 pk;
+  pk.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
+  pk.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+  pk.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
+  pk.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+  return pk;
+}
+
 // ---------------------------------------------------------------------------------------------
-// row workers
+// row workers: thread (row, g) owns columns [g*CW, g*CW+CW) of token row `row` (= TMEM lane), CW = 256 / NSPLIT
 // ---------------------------------------------------------------------------------------------
+constexpr int CW = DIM / NSPLIT;
+
 struct Worker {
   uint8_t* smem;
   uint64_t* bars;
+  const float* vec;     // per-layer vectors in shared memory
   uint32_t tl;          // TMEM address of this warp's lane quarter, column 0
   int lane, q, g, row;
   uint32_t xslot;
 
-  __device__ __forceinline__ float exchange(float mine) {      // value of the other thread that owns this row
-    float* s = reinterpret_cast<float*>(smem + OFF_XCH) + xslot * 256;
+  // all-gather of one float between the NSPLIT threads of a row
+  __device__ __forceinline__ const float* exchange(float mine) {
+    float* s = reinterpret_cast<float*>(smem + OFF_XCH) + xslot * (128 * 4);
     xslot ^= 1;
-    s[row * 2 + g] = mine;
-    bar_sync(1 + q, 64);
-    return s[row * 2 + (g ^ 1)];
+    s[row * 4 + g] = mine;
+    bar_sync(1 + q, 32 * NSPLIT);
+    return s + row * 4;
+  }
+  __device__ __forceinline__ float exchange_sum(float mine) {
+    const float* v = exchange(mine);
+    if constexpr (NSPLIT == 2) return v[0] + v[1];
+    const float4 f = *reinterpret_cast<const float4*>(v);
+    return (f.x + f.y) + (f.z + f.w);
+  }
+  __device__ __forceinline__ float exchange_max(float mine) {
+    const float* v = exchange(mine);
+    if constexpr (NSPLIT == 2) return fmaxf(v[0], v[1]);
+    const float4 f = *reinterpret_cast<const float4*>(v);
+    return fmaxf(fmaxf(f.x, f.y), fmaxf(f.z, f.w));
   }
   __device__ __forceinline__ void arrive(int bar) {             // one arrive per warp, after every lane's fences
     fence_proxy_async_smem();
@@ -120,16 +208,12 @@ struct Worker {
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[bar]);
   }
-  // Statistics are accumulated on chunks as shifted sums (shift = the thread's first element) and merged with the
-  // partner thread by Chan's formula, so one sweep over the row is enough and nothing cancels catastrophically.
+  // Statistics are accumulated as shifted sums (shift = the thread's first element) and merged across the row's threads
+  // by Chan's formula, so one sweep over the row is enough and nothing cancels catastrophically.
   struct Stats {
     float shift, s, ss;
-    bool have;
-    __device__ __forceinline__ void add(const float (&x)[32]) {
-      if (!have) {
-        shift = x[0];
-        have = true;
-      }
+    __device__ __forceinline__ void add(const float (&x)[32], bool first) {
+      if (first) shift = x[0];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float d = x[j] - shift;
@@ -139,54 +223,58 @@ struct Worker {
     }
   };
   __device__ __forceinline__ void finish_stats(const Stats& st, float& mean, float& rstd) {
-    const float mean_g = st.shift + st.s * (1.f / 128.f);
-    const float m2_g = fmaxf(st.ss - st.s * st.s * (1.f / 128.f), 0.f);
-    const float mean_o = exchange(mean_g), m2_o = exchange(m2_g);
-    const float dm = mean_g - mean_o;
-    mean = 0.5f * (mean_g + mean_o);
-    rstd = rsqrtf((m2_g + m2_o + dm * dm * 64.f) * (1.f / DIM) + 1e-5f);
+    constexpr float n = float(CW);
+    const float mean_g = st.shift + st.s * (1.f / n);
+    const float m2_g = fmaxf(st.ss - st.s * st.s * (1.f / n), 0.f);
+    mean = exchange_sum(mean_g) * (1.f / NSPLIT);
+    const float dm = mean_g - mean;
+    const float m2 = exchange_sum(fmaf(dm * dm, n, m2_g));
+    rstd = rsqrtf(m2 * (1.f / DIM) + 1e-5f);
   }
   // Sweep 1 of a LayerNorm whose input already sits in TMEM (x1 after the out-projection, x2 after the MLP).
   __device__ __forceinline__ void stats_from_tmem(float& mean, float& rstd) {
-    Stats st{0.f, 0.f, 0.f, false};
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    Stats st{0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c0 = 0; c0 < CW; c0 += 32) {
       float x[32];
-      tmem_ld32(tl + TM_X + g * 128 + c0, reinterpret_cast<uint32_t(&)[32]>(x));
+      tmem_ld32(tl + TM_X + g * CW + c0, reinterpret_cast<uint32_t(&)[32]>(x));
       tmem_ld_wait();
-      st.add(x);
+      st.add(x, c0 == 0);
     }
     finish_stats(st, mean, rstd);
   }
   // Sweep 2: LN(x) -> A0 (bf16, K-major SW128 panels), x + next_bias -> TMEM; then signal the MMA thread.
-  __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      const float* __restrict__ next_bias) {
-    const int cbase = g * 128;
+  __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, int v_gamma, int v_beta, int v_next_bias) {
+    const int cbase = g * CW;
+    const float nmr = -mean * rstd;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 < CW; c0 += 32) {
       float x[32];
       tmem_ld32(tl + TM_X + cbase + c0, reinterpret_cast<uint32_t(&)[32]>(x));
       tmem_ld_wait();
+      const int col0 = cbase + c0;
+      uint8_t* dst = smem + OFF_A0 + (col0 >> 6) * 16384 + row * 128;
+      const int chunk0 = (col0 & 63) >> 3;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        const int col = cbase + c0 + ch * 8;
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
-        const float* y = &x[ch * 8];
-        uint4 pk;
-        pk.x = pack_bf16x2(fmaf((y[0] - mean) * rstd, g0.x, b0.x), fmaf((y[1] - mean) * rstd, g0.y, b0.y));
-        pk.y = pack_bf16x2(fmaf((y[2] - mean) * rstd, g0.z, b0.z), fmaf((y[3] - mean) * rstd, g0.w, b0.w));
-        pk.z = pack_bf16x2(fmaf((y[4] - mean) * rstd, g1.x, b1.x), fmaf((y[5] - mean) * rstd, g1.y, b1.y));
-        pk.w = pack_bf16x2(fmaf((y[6] - mean) * rstd, g1.z, b1.z), fmaf((y[7] - mean) * rstd, g1.w, b1.w));
-        const int panel = col >> 6, chunk = (col & 63) >> 3;
-        *reinterpret_cast<uint4*>(smem + OFF_A0 + panel * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 gm = *reinterpret_cast<const float4*>(vec + v_gamma + col0 + ch * 8 + j);
+          const float4 bt = *reinterpret_cast<const float4*>(vec + v_beta + col0 + ch * 8 + j);
+          y[j] = fmaf(fmaf(x[ch * 8 + j], rstd, nmr), gm.x, bt.x);
+          y[j + 1] = fmaf(fmaf(x[ch * 8 + j + 1], rstd, nmr), gm.y, bt.y);
+          y[j + 2] = fmaf(fmaf(x[ch * 8 + j + 2], rstd, nmr), gm.z, bt.z);
+          y[j + 3] = fmaf(fmaf(x[ch * 8 + j + 3], rstd, nmr), gm.w, bt.w);
+        }
+        *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(next_bias + cbase + c0 + j));
+        const float4 b = *reinterpret_cast<const float4*>(vec + v_next_bias + col0 + j);
         x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
       }
-      tmem_st32(tl + TM_X + cbase + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
+      tmem_st32(tl + TM_X + col0, reinterpret_cast<const uint32_t(&)[32]>(x));
     }
     tmem_st_wait();
     arrive(B_A0_READY);
@@ -198,46 +286,56 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
   Worker w;
   w.smem = smem;
   w.bars = bars;
+  w.vec = reinterpret_cast<const float*>(smem + OFF_VEC);
   const int wt = threadIdx.x - WORKER_T0;
   w.lane = wt & 31;
   w.q = (threadIdx.x >> 5) & 3;          // TMEM lane quarter = warp index mod 4
-  w.g = wt >> 7;
+  w.g = wt >> 7;                         // which part of the columns
   w.row = w.q * 32 + w.lane;
   w.tl = tmem + (uint32_t(w.q * 32) << 16);
   w.xslot = 0;
   const int q = w.q, g = w.g, row = w.row;
   const uint32_t tl = w.tl;
-  const int n_tok = a.n_tok, spt = a.spt, rows_full = spt * n_tok;
-  const int kblocks = (rows_full + 15) >> 4;                       // 16-column blocks of S / P in use
-  // softmax geometry: this row attends to columns [lo, hi); this warp's rows need blocks [b_lo, b_hi)
-  const int sq = min(row / n_tok, spt - 1);
-  const int lo = sq * n_tok, hi = lo + n_tok;
-  const int t_in_seq = row - (row / n_tok) * n_tok;
-  const int r0 = q * 32, r1 = min(q * 32 + 31, rows_full - 1);
-  const int lo_w = min(r0 / n_tok, spt - 1) * n_tok, hi_w = (min(r1 / n_tok, spt - 1) + 1) * n_tok;
-  const int b_lo = lo_w >> 4, b_hi = (hi_w + 15) >> 4;
-  const int nb0 = (b_hi - b_lo + 1) >> 1;
-  const int my_b0 = g == 0 ? b_lo : b_lo + nb0;
-  const int my_nb = g == 0 ? nb0 : (b_hi - b_lo) - nb0;             // <= 4
+  const float* vec = w.vec;
+  const int n_tok = a.n_tok, slot = a.slot, spt = a.spt;
+  const int seq_in_tile = row >> a.slot_log2, t_in_seq = row & (slot - 1);
+  // softmax geometry.  This row attends to score columns [lo, lo + n_tok).  The warp's rows cover sequences s0..s1, so
+  // the warp sweeps the 8-column chunks [c_lo, c_hi) and the row's threads split them evenly (<= 8 / NSPLIT chunks each).
+  const int lo = seq_in_tile * slot, hi = lo + n_tok;
+  const int s0 = (q * 32) >> a.slot_log2, s1 = (q * 32 + 31) >> a.slot_log2;
+  const int c_lo = (s0 * slot) >> 3, c_hi = (s1 * slot + n_tok + 7) >> 3;
+  constexpr int MAXC = 8 / NSPLIT;
+  const int per = (c_hi - c_lo + NSPLIT - 1) / NSPLIT;
+  const int my_c0 = c_lo + g * per;
+  const int my_nc = max(0, min(per, c_hi - my_c0));
+  // does any chunk of this thread contain a column outside some row's window?  (interior chunks need no mask)
+  const bool warp_one_seq = s0 == s1;
   const float sm_scale = 1.4426950408889634f * rsqrtf(float(DH));
-  uint32_t n_x0 = 0, n_x1 = 0, n_x2 = 0, n_hacc[2] = {0, 0}, n_hfree[2] = {0, 0};
+  uint32_t n_x0 = 0, n_x1 = 0, n_x2 = 0, n_hacc0 = 0, n_hacc1 = 0, n_hfree0 = 0, n_hfree1 = 0;
+  bool vec_loaded = false;
+  Prof pf;
+  pf.start(blockIdx.x == 0 && wt == 0);
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int seqs_here = min(spt, a.n_seq - tile * spt);
-    const int rows_here = seqs_here * n_tok;
-    const size_t grow = size_t(tile) * spt * n_tok + row;           // global token row (IO_ROWS_F32)
+    const bool valid = seq_in_tile < seqs_here && t_in_seq < n_tok;
+    const size_t grow = (size_t(tile) * spt + seq_in_tile) * n_tok + t_in_seq;     // global token row (IO_ROWS_F32)
+
     // ---- tile input: x (+ pos) -> TMEM, statistics of LN1 on the way --------------------------------------
     float mean, rstd;
     {
-      Worker::Stats st{0.f, 0.f, 0.f, false};
-      const bool valid = row < rows_here;
+      Worker::Stats st{0.f, 0.f, 0.f};
+      const float* pp = a.pos != nullptr ? a.pos + t_in_seq * DIM + g * CW : nullptr;
+      float4 p4[8];
+      if (pp != nullptr && valid) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp) + j);
+      }
       if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
-      const int fr = row / n_tok;
-      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
-      const float* src32 = static_cast<const float*>(a.in) + grow * a.ld_in + g * 128;
-      const float* pp = a.pos + t_in_seq * DIM + g * 128;
+      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(seq_in_tile * DIM + g * CW) * n_tok + t_in_seq;
+      const float* src32 = static_cast<const float*>(a.in) + grow * a.ld_in + g * CW;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < CW; c0 += 32) {
         float x[32];
         if (valid) {
           if constexpr (IO == IO_NCHW_BF16) {
@@ -250,202 +348,206 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
               x[j] = x4.x; x[j + 1] = x4.y; x[j + 2] = x4.z; x[j + 3] = x4.w;
             }
           }
-          if (a.pos != nullptr) {
+          if (pp != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + c0 + j));
-              x[j] += p4.x; x[j + 1] += p4.y; x[j + 2] += p4.z; x[j + 3] += p4.w;
+            for (int j = 0; j < 8; ++j) {
+              x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
+            }
+            if (c0 + 32 < CW) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp + c0 + 32) + j);
             }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = 0.f;
         }
-        st.add(x);
-        tmem_st32(tl + TM_X + g * 128 + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
+        st.add(x, c0 == 0);
+        tmem_st32(tl + TM_X + g * CW + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
       }
       tmem_st_wait();
       w.finish_stats(st, mean, rstd);
-      if constexpr (IO == IO_NCHW_BF16) bar_sync(5, 256);   // every worker has read its part of the staged frames out of A0
+      if constexpr (IO == IO_NCHW_BF16) bar_sync(5, NUM_WORKERS);   // every worker has read its part of the staged frames out of A0
     }
+    pf.mark(PW_INPUT);
 
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      w.normalize_from_tmem(mean, rstd, L.ln1_g, L.ln1_b, L.b_out);
+      if (a.depth > 1 || !vec_loaded) {          // per-layer vectors -> shared memory (once per CTA when there is one layer)
+        if (vec_loaded) bar_sync(5, NUM_WORKERS);  // previous layer's readers are done
+        float* vs = reinterpret_cast<float*>(smem + OFF_VEC);
+        for (int i = wt; i < DIM; i += NUM_WORKERS) {
+          vs[V_LN1G + i] = L.ln1_g[i]; vs[V_LN1B + i] = L.ln1_b[i]; vs[V_BOUT + i] = L.b_out[i];
+          vs[V_LN2G + i] = L.ln2_g[i]; vs[V_LN2B + i] = L.ln2_b[i]; vs[V_BFF2 + i] = L.b_ff2[i];
+        }
+        for (int i = wt; i < a.n_chunks * 128; i += NUM_WORKERS) vs[V_BFF1 + i] = L.b_ff1[i];
+        bar_sync(5, NUM_WORKERS);
+        vec_loaded = true;
+      }
+      pf.mark(PW_VEC);
+      w.normalize_from_tmem(mean, rstd, V_LN1G, V_LN1B, V_BOUT);
+      pf.mark(PW_LN1);
 
       // ---- attention: per head  E1 (QKV -> smem), E3 of the previous head (O -> A1), E2 (softmax) -------------
       float inv_l = 0.f;
 #pragma unroll 1
       for (int h = 0; h <= HEADS; ++h) {
-        if (h < HEADS) {
+        if (h < HEADS) {         // E1: D1 = [Q|K|V]_h as 12 chunks of 8 columns, 12 / NSPLIT per thread
           mbar_wait(&bars[B_D1_FULL], h & 1);
           tc_fence_after();
+          pf.mark(PW_WAIT_D1);
+          constexpr int NCH = 12 / NSPLIT;
           const uint32_t sw = uint32_t((row >> 1) & 3);
-          uint8_t* vbuf = smem + OFF_V + (h & 1) * 8192 + row * 64;
-          if (g == 0) {          // Q (cols 0..31) and the first half of K (cols 32..47)
-            uint32_t r[32], r2[16];
-            tmem_ld32(tl + TM_D1, r);
-            tmem_ld16(tl + TM_D1 + 32, r2);
-            tmem_ld_wait();
+          uint32_t r[NCH * 8];
+          if constexpr (NSPLIT == 2) {
+            tmem_ld32(tl + TM_D1 + g * 48, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+            tmem_ld16(tl + TM_D1 + g * 48 + 32, reinterpret_cast<uint32_t(&)[16]>(r[32]));
+          } else {
+            tmem_ld16(tl + TM_D1 + g * 24, reinterpret_cast<uint32_t(&)[16]>(r[0]));
+            tmem_ld8(tl + TM_D1 + g * 24 + 16, reinterpret_cast<uint32_t(&)[8]>(r[16]));
+          }
+          tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-              *reinterpret_cast<uint4*>(smem + OFF_Q + row * 64 + ((uint32_t(c) ^ sw) << 4)) = pk;
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(r2[c * 8 + 0]), __uint_as_float(r2[c * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(r2[c * 8 + 2]), __uint_as_float(r2[c * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(r2[c * 8 + 4]), __uint_as_float(r2[c * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(r2[c * 8 + 6]), __uint_as_float(r2[c * 8 + 7]));
-              *reinterpret_cast<uint4*>(smem + OFF_K + row * 64 + ((uint32_t(c) ^ sw) << 4)) = pk;
-            }
-          } else {               // second half of K (cols 48..63) and V (cols 64..95)
-            uint32_t r[32], r2[16];
-            tmem_ld16(tl + TM_D1 + 48, r2);
-            tmem_ld32(tl + TM_D1 + 64, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(r2[c * 8 + 0]), __uint_as_float(r2[c * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(r2[c * 8 + 2]), __uint_as_float(r2[c * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(r2[c * 8 + 4]), __uint_as_float(r2[c * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(r2[c * 8 + 6]), __uint_as_float(r2[c * 8 + 7]));
-              *reinterpret_cast<uint4*>(smem + OFF_K + row * 64 + ((uint32_t(c + 2) ^ sw) << 4)) = pk;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
-              pk.y = pack_bf16x2(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
-              pk.z = pack_bf16x2(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
-              pk.w = pack_bf16x2(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
-              *reinterpret_cast<uint4*>(vbuf + ((uint32_t(c) ^ sw) << 4)) = pk;
-            }
+          for (int c = 0; c < NCH; ++c) {
+            const int id = g * NCH + c;                    // 0..3 Q, 4..7 K, 8..11 V
+            uint8_t* base = id < 4 ? smem + OFF_Q : (id < 8 ? smem + OFF_K : smem + OFF_V + (h & 1) * 8192);
+            *reinterpret_cast<uint4*>(base + row * 64 + ((uint32_t(id & 3) ^ sw) << 4)) = pack8u(&r[c * 8]);
           }
           w.arrive(B_STAGED);
+          pf.mark(PW_E1);
         }
-        if (h > 0) {             // E3 of head h-1: O / l -> bf16 -> A1 columns [(h-1)*32, +32)
+        if (h > 0) {             // E3 of head h-1: O / l -> bf16 -> A1 columns [(h-1)*32 + g*OW, +OW)
           mbar_wait(&bars[B_O_FULL], (h - 1) & 1);
           tc_fence_after();
-          uint32_t r[16];
-          tmem_ld16(tl + TM_O + g * 16, r);
+          pf.mark(PW_WAIT_O);
+          constexpr int OW = DH / NSPLIT;                  // 16 or 8 columns
+          uint32_t r[OW];
+          if constexpr (OW == 16) tmem_ld16(tl + TM_O + g * OW, reinterpret_cast<uint32_t(&)[16]>(r[0]));
+          else tmem_ld8(tl + TM_O + g * OW, reinterpret_cast<uint32_t(&)[8]>(r[0]));
           tmem_ld_wait();
-          const int col = (h - 1) * DH + g * 16;
+          const int col = (h - 1) * DH + g * OW;
           const int panel = col >> 6, chunk = (col & 63) >> 3;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(r[c * 8 + 0]) * inv_l, __uint_as_float(r[c * 8 + 1]) * inv_l);
-            pk.y = pack_bf16x2(__uint_as_float(r[c * 8 + 2]) * inv_l, __uint_as_float(r[c * 8 + 3]) * inv_l);
-            pk.z = pack_bf16x2(__uint_as_float(r[c * 8 + 4]) * inv_l, __uint_as_float(r[c * 8 + 5]) * inv_l);
-            pk.w = pack_bf16x2(__uint_as_float(r[c * 8 + 6]) * inv_l, __uint_as_float(r[c * 8 + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(smem + OFF_A1 + panel * 16384 + row * 128 + (((chunk + c) ^ (row & 7)) << 4)) = pk;
+          for (int c = 0; c < OW / 8; ++c) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[c * 8 + j]) * inv_l;
+            *reinterpret_cast<uint4*>(smem + OFF_A1 + panel * 16384 + row * 128 + (((chunk + c) ^ (row & 7)) << 4)) = pack8(y);
           }
           w.arrive(B_O_DRAINED);
+          pf.mark(PW_E3);
         }
-        if (h < HEADS) {         // E2: masked softmax of this row over its own sequence, P (bf16) over the S columns
+        if (h < HEADS) {         // E2: softmax of this row over its own sequence's columns, P (bf16) over the S columns
           mbar_wait(&bars[B_S_FULL], h & 1);
           tc_fence_after();
-          float s[4][16];
+          pf.mark(PW_WAIT_S);
+          float s[MAXC][8];
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (b < my_nb) tmem_ld16(tl + TM_S + (my_b0 + b) * 16, reinterpret_cast<uint32_t(&)[16]>(s[b]));
+          for (int c = 0; c < MAXC; ++c)
+            if (c < my_nc) tmem_ld8(tl + TM_S + (my_c0 + c) * 8, reinterpret_cast<uint32_t(&)[8]>(s[c]));
           tmem_ld_wait();
           float mx = -INFINITY;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < my_nc) {
+              const int col0 = (my_c0 + c) * 8;
+              if (!warp_one_seq || col0 + 8 > hi) {        // boundary chunk (or a warp that spans sequences): mask per column
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = (my_b0 + b) * 16 + j;
-              const bool ok = (b < my_nb) && col >= lo && col < hi;
-              s[b][j] = ok ? s[b][j] * sm_scale : -INFINITY;
-              mx = fmaxf(mx, s[b][j]);
+                for (int j = 0; j < 8; ++j) s[c][j] = (col0 + j >= lo && col0 + j < hi) ? s[c][j] : -INFINITY;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) mx = fmaxf(mx, s[c][j]);
             }
           }
-          mx = fmaxf(mx, w.exchange(mx));      // also orders every S load of the row pair before any P store
+          mx = w.exchange_max(mx);             // also orders every S load of the row before any P store
+          const float nmx = -mx * sm_scale;
           float sum = 0.f;
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            if (b < my_nb) {
-              uint32_t pk[8];
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < my_nc) {
+              float p[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float p0 = fast_exp2(s[b][j] - mx), p1 = fast_exp2(s[b][j + 1] - mx);
-                sum += p0 + p1;
-                pk[j >> 1] = pack_bf16x2(p0, p1);
+              for (int j = 0; j < 8; ++j) {
+                p[j] = fast_exp2(fmaf(s[c][j], sm_scale, nmx));
+                sum += p[j];
               }
-              tmem_st8(tl + TM_S + (my_b0 + b) * 8, pk);
+              tmem_st4(tl + TM_S + (my_c0 + c) * 4, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
             }
           }
-          {                      // P columns the MMA reads but no row of this warp uses: zeros
-            const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const int zb0 = g == 0 ? 0 : b_hi, zb1 = g == 0 ? b_lo : kblocks;
-            for (int b = zb0; b < zb1; ++b) tmem_st8(tl + TM_S + b * 8, z);
-          }
-          sum += w.exchange(sum);
-          inv_l = 1.f / sum;
+          // P columns the MMA reads (all 128) but this warp's rows never use: zeros (split between the row's threads)
+          for (int c = g; c < 16; c += NSPLIT)
+            if (c < c_lo || c >= c_hi) tmem_st4(tl + TM_S + c * 4, 0u, 0u, 0u, 0u);
+          inv_l = 1.f / w.exchange_sum(sum);
           tmem_st_wait();
           w.arrive(B_P_READY);
+          pf.mark(PW_E2);
         }
       }
 
       // ---- LN2 on x1 = x + attention (accumulated in TMEM by the out-projection) ------------------------------
       mbar_wait(&bars[B_X1_FULL], (n_x1++) & 1);
       tc_fence_after();
+      pf.mark(PW_WAIT_X1);
       w.stats_from_tmem(mean, rstd);
-      w.normalize_from_tmem(mean, rstd, L.ln2_g, L.ln2_b, L.b_ff2);
+      w.normalize_from_tmem(mean, rstd, V_LN2G, V_LN2B, V_BFF2);
+      pf.mark(PW_LN2);
 
       // ---- MLP: per 128-column chunk of the hidden layer, bias + tanh-GELU -> bf16 A operand ---------------------
 #pragma unroll 1
       for (int c = 0; c < a.n_chunks; ++c) {
         const int b = c & 1;
-        mbar_wait(&bars[B_HACC_FULL + b], (n_hacc[b]++) & 1);
-        if (c >= 2) mbar_wait(&bars[B_HBUF_FREE + b], (n_hfree[b]++) & 1);
+        if (b == 0) {
+          mbar_wait(&bars[B_HACC_FULL], (n_hacc0++) & 1);
+          if (c >= 2) mbar_wait(&bars[B_HBUF_FREE], (n_hfree0++) & 1);
+        } else {
+          mbar_wait(&bars[B_HACC_FULL1], (n_hacc1++) & 1);
+          if (c >= 2) mbar_wait(&bars[B_HBUF_FREE1], (n_hfree1++) & 1);
+        }
         tc_fence_after();
-        const float* bias = L.b_ff1 + c * 128 + g * 64;
-        uint8_t* dst = smem + OFF_A1 + b * 32768 + g * 16384 + row * 128;
+        pf.mark(PW_WAIT_HACC);
+        constexpr int HW = 128 / NSPLIT;                   // hidden columns per thread: 64 or 32
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = 0; c0 < HW; c0 += 32) {
+          const int hc = g * HW + c0;                      // column within the 128-wide chunk
+          const float* bias = vec + V_BFF1 + c * 128 + hc;
+          uint8_t* dst = smem + OFF_A1 + b * 32768 + (hc >> 6) * 16384 + row * 128;
+          const int chunk0 = (hc & 63) >> 3;
           uint32_t r[32];
-          tmem_ld32(tl + (b ? TM_H1 : TM_H0) + g * 64 + c0, r);
+          tmem_ld32(tl + (b ? TM_H1 : TM_H0) + hc, r);
           tmem_ld_wait();
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + ch * 8 + 4));
-            uint4 pk;
-            pk.x = pack_bf16x2(gelu_tanh<true>(__uint_as_float(r[ch * 8 + 0]) + b0.x), gelu_tanh<true>(__uint_as_float(r[ch * 8 + 1]) + b0.y));
-            pk.y = pack_bf16x2(gelu_tanh<true>(__uint_as_float(r[ch * 8 + 2]) + b0.z), gelu_tanh<true>(__uint_as_float(r[ch * 8 + 3]) + b0.w));
-            pk.z = pack_bf16x2(gelu_tanh<true>(__uint_as_float(r[ch * 8 + 4]) + b1.x), gelu_tanh<true>(__uint_as_float(r[ch * 8 + 5]) + b1.y));
-            pk.w = pack_bf16x2(gelu_tanh<true>(__uint_as_float(r[ch * 8 + 6]) + b1.z), gelu_tanh<true>(__uint_as_float(r[ch * 8 + 7]) + b1.w));
-            *reinterpret_cast<uint4*>(dst + (((c0 >> 3) + ch) ^ (row & 7)) * 16) = pk;
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 8 + j);
+              y[j] = gelu_fast(__uint_as_float(r[ch * 8 + j]) + b4.x);
+              y[j + 1] = gelu_fast(__uint_as_float(r[ch * 8 + j + 1]) + b4.y);
+              y[j + 2] = gelu_fast(__uint_as_float(r[ch * 8 + j + 2]) + b4.z);
+              y[j + 3] = gelu_fast(__uint_as_float(r[ch * 8 + j + 3]) + b4.w);
+            }
+            *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
           }
         }
         w.arrive(B_H_READY + b);
+        pf.mark(PW_GELU);
       }
 
       // ---- x2 = x1 + MLP, accumulated in TMEM by the second MLP GEMM --------------------------------------------
       mbar_wait(&bars[B_X2_FULL], (n_x2++) & 1);
       tc_fence_after();
+      pf.mark(PW_WAIT_X2);
       if (l + 1 < a.depth) w.stats_from_tmem(mean, rstd);
     }
 
     // ---- tile output ----------------------------------------------------------------------------
     {
-      const bool valid = row < rows_here;
-      const int fr = row / n_tok;
-      __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(smem + OFF_A1) + size_t(fr * DIM + g * 128) * n_tok + t_in_seq;
-      float* dst32 = static_cast<float*>(a.out) + grow * a.ld_out + g * 128;
+      __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(smem + OFF_A1) + size_t(seq_in_tile * DIM + g * CW) * n_tok + t_in_seq;
+      float* dst32 = static_cast<float*>(a.out) + grow * a.ld_out + g * CW;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < CW; c0 += 32) {
         float x[32];
-        tmem_ld32(tl + TM_X + g * 128 + c0, reinterpret_cast<uint32_t(&)[32]>(x));
+        tmem_ld32(tl + TM_X + g * CW + c0, reinterpret_cast<uint32_t(&)[32]>(x));
         tmem_ld_wait();
         if (valid) {
           if constexpr (IO == IO_NCHW_BF16) {
@@ -459,14 +561,18 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       }
       if constexpr (IO == IO_NCHW_BF16) {
         fence_proxy_async_smem();
-        bar_sync(5, 256);
+        bar_sync(5, NUM_WORKERS);
         if (threadIdx.x == WORKER_T0) {
           __nv_bfloat16* gdst = static_cast<__nv_bfloat16*>(a.out) + size_t(tile) * spt * n_tok * DIM;
-          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(rows_here) * DIM * 2);
+          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(seqs_here) * n_tok * DIM * 2);
           bulk_wait_read0();     // A1 is written again by the next tile's attention (ordered by the bar_sync after its input sweep)
         }
       }
     }
+    pf.mark(PW_OUTPUT);
+#ifdef AVF_FUSED_PROF
+    if (pf.on) g_prof[PW_TILES] += 1;
+#endif
   }
   if constexpr (IO == IO_NCHW_BF16) {
     if (threadIdx.x == WORKER_T0) bulk_wait_all0();
@@ -559,15 +665,19 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   const uint32_t a0 = smem_u32(smem + OFF_A0), a1 = smem_u32(smem + OFF_A1);
   const uint32_t qs = smem_u32(smem + OFF_Q), ks = smem_u32(smem + OFF_K), vs = smem_u32(smem + OFF_V);
   const uint32_t ring = smem_u32(smem + OFF_RING);
-  const int rows_full = a.spt * a.n_tok;
-  const int kmax = ((rows_full + 15) >> 4) << 4;
+  const int kmax = 128;                        // S / P span the whole tile: sequences sit in power-of-two row slots
   const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, kmax), id_pv = make_idesc_bf16(128, DH, 0, 1),
                  id_128 = make_idesc_bf16(128, 128);
   uint32_t it = 0, n_a0 = 0, n_hready[2] = {0, 0};
+  Prof pf;
+  pf.start(blockIdx.x == 0);
+  int ring_phase = PM_QKV;
   auto slot_wait = [&]() -> uint32_t {
     const uint32_t s = it % RING, ph = (it / RING) & 1;
+    pf.mark(ring_phase);
     mbar_wait(&bars[B_RING_FULL + s], ph);
     tc_fence_after();
+    pf.mark(PM_RINGWAIT);
     return ring + s * SLOT_BYTES;
   };
   auto slot_release = [&]() {
@@ -603,26 +713,36 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       last_layer = l == a.depth - 1;
       mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
       tc_fence_after();
+      pf.mark(PM_WAIT_A0);
+      ring_phase = PM_QKV;
       qkv();
+      pf.mark(PM_QKV);
       for (int h = 0; h < HEADS; ++h) {
         mbar_wait(&bars[B_STAGED], h & 1);
         tc_fence_after();
+        pf.mark(PM_WAIT_STAGED);
         {                                     // S[128 x kmax] = Q_h K_h^T
           const uint64_t da = desc_sw64(qs), db = desc_sw64(ks);
           umma_bf16(tmem + TM_S, da, db, id_s, 0u);
           umma_bf16(tmem + TM_S, da + 2, db + 2, id_s, 1u);
           umma_commit(&bars[B_S_FULL]);
         }
+        pf.mark(PM_S);
         if (h + 1 < HEADS) qkv();
+        pf.mark(PM_QKV);
         mbar_wait(&bars[B_P_READY], h & 1);
         if (h > 0) mbar_wait(&bars[B_O_DRAINED], (h - 1) & 1);
         tc_fence_after();
+        pf.mark(PM_WAIT_P);
         for (int k = 0; k < kmax / 16; ++k)   // O[128 x 32] = P V_h   (A from TMEM, B MN-major)
           umma_bf16_ts(tmem + TM_O, tmem + TM_S + uint32_t(k * 8), desc_sw64(vs + (h & 1) * 8192 + k * 1024), id_pv, k != 0 ? 1u : 0u);
         umma_commit(&bars[B_O_FULL]);
+        pf.mark(PM_PV);
       }
       mbar_wait(&bars[B_O_DRAINED], (HEADS - 1) & 1);
       tc_fence_after();
+      pf.mark(PM_WAIT_OD7);
+      ring_phase = PM_OUT;
       for (int kp = 0; kp < 4; ++kp)          // x += attn Wout^T  (x + b_out was stored by the workers)
         for (int nh = 0; nh < 2; ++nh) {
           const uint32_t sb = slot_wait();
@@ -632,15 +752,21 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
           slot_release();
         }
       umma_commit(&bars[B_X1_FULL]);
+      pf.mark(PM_OUT);
 
       mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
       tc_fence_after();
+      pf.mark(PM_WAIT_A0B);
+      ring_phase = PM_FF1;
       ff1(0);
       if (a.n_chunks > 1) ff1(1);
       for (int c = 0; c < a.n_chunks; ++c) {
         const int b = c & 1;
+        pf.mark(PM_FF1);
         mbar_wait(&bars[B_H_READY + b], (n_hready[b]++) & 1);
         tc_fence_after();
+        pf.mark(PM_WAIT_H);
+        ring_phase = PM_FF2;
         for (int kp = 0; kp < 2; ++kp)        // x += gelu(H_c) W2[:, c*128..]^T
           for (int nh = 0; nh < 2; ++nh) {
             const uint32_t sb = slot_wait();
@@ -649,6 +775,8 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
             for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
             slot_release();
           }
+        pf.mark(PM_FF2);
+        ring_phase = PM_FF1;
         if (c + 2 < a.n_chunks) {
           umma_commit(&bars[B_HBUF_FREE + b]);
           ff1(c + 2);
@@ -680,7 +808,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
     }
     for (int i = 0; i < NUM_BARS; ++i) {
       const bool by_workers = i == B_A0_READY || i == B_STAGED || i == B_P_READY || i == B_O_DRAINED || i == B_H_READY || i == B_H_READY1;
-      mbar_init(&bars[i], by_workers ? 8 : 1);
+      mbar_init(&bars[i], by_workers ? NUM_WORKERS / 32 : 1);
     }
     fence_barrier_init();
   }
@@ -717,8 +845,23 @@ int sm_count_cached() {
 
 }  // namespace
 
+int fused_prof_read(unsigned long long* out64, int reset) {
+#ifdef AVF_FUSED_PROF
+  AVF_CUDA(cudaDeviceSynchronize());
+  AVF_CUDA(cudaMemcpyFromSymbol(out64, g_prof, sizeof(unsigned long long) * 64));
+  if (reset) {
+    static unsigned long long zeros[64] = {0};
+    AVF_CUDA(cudaMemcpyToSymbol(g_prof, zeros, sizeof(zeros)));
+  }
+  return 0;
+#else
+  (void)out64; (void)reset;
+  return AVF_EUNSUPPORTED;
+#endif
+}
+
 bool encoder_fused_supported(const avf_stack_shape* s) {
-  return s->dim == DIM && s->heads == HEADS && s->dim_head == DH && s->mlp_dim % 128 == 0 && s->mlp_dim >= 128 && s->n_tok >= 1 &&
+  return s->dim == DIM && s->heads == HEADS && s->dim_head == DH && s->mlp_dim % 128 == 0 && s->mlp_dim >= 128 && s->mlp_dim <= MAX_MLP && s->n_tok >= 1 &&
          s->n_tok <= 64 && s->depth >= 1 && s->depth <= MAX_DEPTH;
 }
 
@@ -732,7 +875,10 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
   static thread_local FusedArgs a;      // ~2 KB of tensor maps + pointers, passed by value (__grid_constant__) per launch
   static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
   a.in = in; a.out = out; a.pos = pos; a.ld_in = ld_in; a.ld_out = ld_out;
-  a.n_seq = s->n_seq; a.n_tok = s->n_tok; a.spt = 128 / s->n_tok;
+  a.n_seq = s->n_seq; a.n_tok = s->n_tok;
+  a.slot = 16; a.slot_log2 = 4;
+  while (a.slot < s->n_tok) { a.slot *= 2; ++a.slot_log2; }
+  a.spt = 128 / a.slot;
   a.n_tiles = ceil_div(s->n_seq, a.spt);
   a.n_chunks = s->mlp_dim / 128; a.depth = s->depth;
   const int inner = HEADS * DH;
