@@ -39,7 +39,8 @@ enum { AVF_FP32 = 0, AVF_BF16 = 1 };                 /* compute mode / storage d
 enum { AVF_EINVAL = -1, AVF_ENODEVICE = -2, AVF_EWORKSPACE = -3, AVF_EUNSUPPORTED = -4 };
 
 /* epilogue flags of avf_linear_fwd */
-enum { AVF_EPI_BIAS = 1, AVF_EPI_GELU = 2, AVF_EPI_RESIDUAL = 4 };
+enum { AVF_EPI_BIAS = 1, AVF_EPI_GELU = 2, AVF_EPI_RESIDUAL = 4, AVF_EPI_DGELU = 8 /* x gelu'(aux), training */,
+       AVF_EPI_SAVE_PRE = 16 /* store the pre-GELU value (after bias) to aux, training */ };
 
 /* One pre-LN encoder layer (models/heads.py:246-250).  Weight matrices are [out, in] row-major
  * exactly as nn.Linear stores them; `w_dtype` says whether they are fp32 or bf16 copies
@@ -115,7 +116,8 @@ int avf_attention_fwd(int io_mode, const void* qkv, void* out, int32_t n_seq, in
                       int32_t heads, int32_t dim_head, void* stream);
 
 /* ---- a6: SFormer token (un)packing, models/vformer.py:247-253 and :257-259 ---------------- */
-/* fmap [n_frames, dim, hw] (NCHW, fp32 or bf16 per io_mode) -> x [n_frames*hw, dim] fp32 + pos[hw, dim] */
+/* fmap [n_frames, dim, hw] (NCHW, fp32 or bf16 per io_mode) -> x [n_frames*hw, dim] fp32 + pos[hw, dim]
+ * (pos == NULL: plain transpose — the backward of avf_sformer_tokens_unpack) */
 int avf_sformer_tokens_pack(int io_mode, const void* fmap, const float* pos, float* x,
                             int32_t n_frames, int32_t dim, int32_t hw, void* stream);
 int avf_sformer_tokens_unpack(int io_mode, const float* x, void* fmap,
@@ -161,6 +163,90 @@ int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);
 /* x[r,:] += pos[r % period, :] */
 int avf_add_row_periodic(float* x, int32_t ld_x, const float* pos, int32_t rows, int32_t dim, int32_t period, void* stream);
+
+/* ============================================================================================
+ * Training (train.py:206-236 restricted to the transformer stack): loss.backward() through the
+ * drop-in modules lands here.  bf16 mode keeps GEMM operands (activations on the tape, gradient
+ * operands, weights) in bf16 and everything else — residual / gradient streams, statistics,
+ * reductions, weight gradients, optimiser state — in fp32.  All reductions have a fixed order.
+ * ============================================================================================ */
+
+/* Gradient destinations of one layer, same field order as avf_layer_weights; every buffer is fp32 with the shape
+ * of its parameter and is OVERWRITTEN.  A NULL field skips that gradient (frozen parameter). */
+typedef struct avf_layer_grads {
+  float* ln1_gamma; float* ln1_beta; float* w_qkv; float* w_out; float* b_out;
+  float* ln2_gamma; float* ln2_beta; float* w_ff1; float* b_ff1; float* w_ff2; float* b_ff2;
+} avf_layer_grads;
+
+/* General GEMM behind every linear of the forward and backward pass:  C[M,N] = epi(op(A) op(B)).
+ *   trans_a = 0: A is [M,K] row-major (lda);   1: A is stored [K,M] row-major.
+ *   trans_b = 0: B is [N,K] row-major (nn.Linear layout: C = A B^T);   1: B is stored [K,N] row-major.
+ * so  forward  Y = X W^T (0,0);  dgrad  dX = dY W (0,1, B = W itself);  wgrad  dW = dY^T X (1,1, K = token rows).
+ * mode BF16: operands bf16 on tcgen05 (operands with the reduction index as row index are fed as MN-major tiles, no
+ * transposed copy); the (1,1) form splits K over the SMs and needs avf_gemm_workspace_bytes() of scratch, writes plain
+ * fp32.  mode FP32: CUDA cores.  `aux` [M, ld_aux] (bf16 / fp32 per mode): AVF_EPI_SAVE_PRE stores the pre-GELU value
+ * there, AVF_EPI_DGELU multiplies the accumulator by gelu'(aux) before anything else. */
+size_t avf_gemm_workspace_bytes(int mode, int trans_a, int trans_b, int32_t m, int32_t n, int32_t k);
+int avf_gemm(int mode, int trans_a, int trans_b, const void* a, int32_t lda, const void* b, int32_t ldb,
+             const float* bias, const float* residual, int32_t ld_res, void* aux, int32_t ld_aux,
+             void* c, int32_t ldc, int c_mode, int32_t m, int32_t n, int32_t k, int epilogue_flags,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Encoder stack, forward with an activation tape (x is NOT modified; the result goes to out, row stride ld_out)
+ * and backward.  dx [n_seq*n_tok, dim] dense fp32 holds the gradient wrt the stack output on entry and the gradient
+ * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted). */
+size_t avf_encoder_tape_bytes(const avf_stack_shape* s, int mode);
+size_t avf_encoder_bwd_workspace_bytes(const avf_stack_shape* s, int mode);
+int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
+                                const float* x, int32_t ld_x, float* out, int32_t ld_out,
+                                void* tape, size_t tape_bytes, void* stream);
+int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
+                          const void* tape, size_t tape_bytes, float* dx, int32_t ld_dx,
+                          const avf_layer_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Building blocks of the backward pass (exposed for tests). */
+/* out[c] = sum_r x[r, c]; x is fp32 or bf16 per in_mode with row stride ld (elements). */
+size_t avf_colsum_workspace_bytes(int32_t rows, int32_t cols);
+int avf_colsum(int in_mode, const void* x, size_t ld, int32_t rows, int32_t cols, float* out,
+               void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of y = x + f(LN(x)): dres (in: dL/dy, out: dL/dx) += LN'(dy_norm); optional bf16 copy of the result;
+ * dgamma / dbeta of the LayerNorm and dbias = column sums of the incoming dres (bias gradient of f's last linear). */
+size_t avf_layernorm_bwd_workspace_bytes(int32_t rows, int32_t dim);
+int avf_layernorm_bwd(const float* x, int32_t ld_x, const float* gamma, const float* dy_norm, float* dres, int32_t ld_d,
+                      void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int32_t rows, int32_t dim,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* dqkv [rows, 3*heads*dh] from qkv and dout [rows, heads*dh] (softmax recomputed). */
+int avf_attention_bwd(int io_mode, const void* qkv, const void* dout, void* dqkv, int32_t n_seq, int32_t n_tok,
+                      int32_t heads, int32_t dim_head, void* stream);
+
+/* AU_former front end for training.  batch_stats = 1: BatchNorm1d uses batch statistics and updates the running
+ * ones in place with `momentum` (nn.BatchNorm1d in train()); 0: running statistics (eval(), or a frozen model). */
+size_t avf_au_former_front_tape_bytes(int mode, int32_t n_clips, int32_t in_dim);
+int avf_au_former_front_fwd_train(int mode, const float* emb, int32_t ld_emb,
+                                  const float* bn_gamma, const float* bn_beta, float* bn_mean, float* bn_var,
+                                  int batch_stats, float momentum, const void* w_cat, const float* b_cat, const float* pos,
+                                  float* x, int32_t n_clips, int32_t in_dim, int32_t emb_dim,
+                                  void* tape, size_t tape_bytes, void* stream);
+size_t avf_au_former_front_bwd_workspace_bytes(int mode, int32_t n_clips, int32_t in_dim, int32_t emb_dim);
+/* dx [n_clips*12, emb_dim] fp32 dense -> demb [n_clips, in_dim] (row stride ld_demb), dbn_gamma, dbn_beta [in_dim],
+ * dw_cat [12*emb_dim, in_dim], db_cat [12*emb_dim] (== the gradient of pos_embedding).  Any output may be NULL. */
+int avf_au_former_front_bwd(int mode, const float* emb, int32_t ld_emb, const float* bn_gamma,
+                            const float* bn_mean, const float* bn_var, int batch_stats, const void* w_cat,
+                            const void* tape, size_t tape_bytes, const float* dx,
+                            float* demb, int32_t ld_demb, float* dbn_gamma, float* dbn_beta, float* dw_cat, float* db_cat,
+                            int32_t n_clips, int32_t in_dim, int32_t emb_dim,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of avf_au_logits_fwd: dx[c*12+i,:] = dlogits[c,i] w_last[i,:]; dw_last[i,:] = sum_c dlogits[c,i] x[c*12+i,:]. */
+int avf_au_logits_bwd(const float* dlogits, int32_t ld_dlogits, const float* x, int32_t ld_x, const float* w_last,
+                      float* dx, int32_t ld_dx, float* dw_last, int32_t n_clips, int32_t dim, void* stream);
+
+/* One Adam step on a flat fp32 bucket (train.py:334: torch.optim.Adam, weight decay coupled into the gradient;
+ * decoupled = 1 gives AdamW).  grads are multiplied by grad_scale first (1/world_size after a sum all-reduce).
+ * bf16_shadow (optional) receives the updated parameters as bf16.  step counts from 1. */
+int avf_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, size_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, int decoupled,
+                  float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

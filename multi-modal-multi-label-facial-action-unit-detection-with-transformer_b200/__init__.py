@@ -6,21 +6,24 @@ Public surface mirrors the reference's model files:
     AU_former, former_AU_head / tformer_AU_head                    (models/heads.py, models/tformer.py)
     Transformer, Attention, FeedForward, PreNorm, Residual, GELU   (models/heads.py:164-256)
     AULoss                                                         (models/loss.py:63-103)
-plus ``functional`` (tensor-level wrappers of the C ABI), ``dp`` (data-parallel sharding helpers)
-and ``build()``.
+plus ``functional`` (tensor-level wrappers of the C ABI), ``autograd`` (the backward bridges), ``FusedAdam``
+(train.py:334's optimiser as one kernel over a flat bucket), ``dp`` (data-parallel sharding helpers) and ``build()``.
 """
 from . import _lib
 from . import functional
+from . import autograd
+from . import optim
 from ._lib import build
 from .audio import AudioModel
 from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, load_pretrain
 from .encoder import GELU, Attention, FeedForward, PreNorm, Residual, Transformer, default_precision, set_default_precision
 from .heads import AU_former, former_AU_head, tformer_AU_head
 from .loss import AULoss
+from .optim import FusedAdam
 from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
 
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "AudioModel", "functional", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "AudioModel", "FusedAdam", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]

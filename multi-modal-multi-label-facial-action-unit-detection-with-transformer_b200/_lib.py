@@ -19,11 +19,11 @@ LIB_PATH = os.path.join(_PKG, "libavformer_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-t", "0",
 ]
 
 AVF_FP32, AVF_BF16 = 0, 1
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL = 1, 2, 4
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_DGELU, EPI_SAVE_PRE = 1, 2, 4, 8, 16
 
 _c_p = ctypes.c_void_p
 _i32 = ctypes.c_int32
@@ -34,6 +34,11 @@ class LayerWeights(ctypes.Structure):
     """struct avf_layer_weights (include/avformer_b200.h)."""
     _fields_ = [(n, _c_p) for n in ("ln1_gamma", "ln1_beta", "w_qkv", "w_out", "b_out", "ln2_gamma", "ln2_beta",
                                     "w_ff1", "b_ff1", "w_ff2", "b_ff2")]
+
+
+class LayerGrads(ctypes.Structure):
+    """struct avf_layer_grads: fp32 gradient destinations, NULL = not wanted."""
+    _fields_ = LayerWeights._fields_
 
 
 class StackShape(ctypes.Structure):
@@ -71,6 +76,29 @@ SIGNATURES = {
     "avf_cast_f32_to_bf16": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_cast_bf16_to_f32": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_add_row_periodic": (ctypes.c_int, [_c_p, _i32, _c_p, _i32, _i32, _i32, _c_p]),
+    # ---- training ----
+    "avf_gemm_workspace_bytes": (_sz, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32, _i32, _i32]),
+    "avf_gemm": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_p, _i32, _c_p, _i32, _c_p, _c_p, _i32, _c_p, _i32, _c_p, _i32,
+                                ctypes.c_int, _i32, _i32, _i32, ctypes.c_int, _c_p, _sz, _c_p]),
+    "avf_encoder_tape_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
+    "avf_encoder_bwd_workspace_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
+    "avf_encoder_stack_fwd_train": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _i32, _c_p, _i32,
+                                                   _c_p, _sz, _c_p]),
+    "avf_encoder_stack_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _sz, _c_p, _i32,
+                                             ctypes.POINTER(LayerGrads), _c_p, _sz, _c_p]),
+    "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
+    "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
+    "avf_layernorm_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "avf_layernorm_bwd": (ctypes.c_int, [_c_p, _i32, _c_p, _c_p, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _c_p, _sz, _c_p]),
+    "avf_attention_bwd": (ctypes.c_int, [ctypes.c_int, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32, _c_p]),
+    "avf_au_former_front_tape_bytes": (_sz, [ctypes.c_int, _i32, _i32]),
+    "avf_au_former_front_fwd_train": (ctypes.c_int, [ctypes.c_int, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, ctypes.c_int, ctypes.c_float, _c_p, _c_p,
+                                                     _c_p, _c_p, _i32, _i32, _i32, _c_p, _sz, _c_p]),
+    "avf_au_former_front_bwd_workspace_bytes": (_sz, [ctypes.c_int, _i32, _i32, _i32]),
+    "avf_au_former_front_bwd": (ctypes.c_int, [ctypes.c_int, _c_p, _i32, _c_p, _c_p, _c_p, ctypes.c_int, _c_p, _c_p, _sz, _c_p, _c_p, _i32,
+                                               _c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p, _sz, _c_p]),
+    "avf_au_logits_bwd": (ctypes.c_int, [_c_p, _i32, _c_p, _i32, _c_p, _c_p, _i32, _c_p, _i32, _i32, _c_p]),
+    "avf_adam_step": (ctypes.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _sz] + [ctypes.c_float] * 5 + [_i32, ctypes.c_int, ctypes.c_float, _c_p]),
 }
 
 _lock = threading.Lock()

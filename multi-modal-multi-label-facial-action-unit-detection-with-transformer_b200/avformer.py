@@ -10,7 +10,7 @@ from torch import nn
 
 from . import functional as AF
 from .audio import AudioModel
-from .encoder import Transformer, _check_inference
+from .encoder import Transformer, needs_grad
 from .heads import AU_former, former_AU_head
 from .loss import AULoss
 from .video import Dummy, VideoModel
@@ -32,7 +32,6 @@ class AudioFormer(nn.Module):
         self.au_head = AU_former(dropout=0.2)
 
     def forward(self, x):
-        _check_inference(self, x)
         feat = self.audio_model(x)
         return self.au_head(feat)[1]
 
@@ -48,7 +47,6 @@ class VisualFormer(nn.Module):
         self.video_model.fc = Dummy()
 
     def forward(self, x):
-        _check_inference(self, x)
         return self.au_head(self.video_model(x))[1]
 
 
@@ -100,11 +98,12 @@ class TwoStreamAuralVisualFormer(nn.Module):
     # -- forward ------------------------------------------------------------------------------
     def forward(self, x):
         audio, clip = x["audio_features"], x["clip"]
-        _check_inference(self, clip)
         AF._cuda(clip, "x['clip']")
         AF._cuda(audio, "x['audio_features']")
         bs = clip.shape[0]
         vm = self.video_model.video_model
+        if needs_grad(self, clip, audio):
+            return self._forward_train(clip, audio)
         # audio: ResNet-18 (torch) -> AU_former, written into columns [0,128) of the fusion input
         fused = torch.empty((bs * 12, 256), dtype=torch.float32, device=clip.device)
         a_feat = self.audio_model.audio_model(audio).float().contiguous()
@@ -116,6 +115,44 @@ class TwoStreamAuralVisualFormer(nn.Module):
         if self.task != "AU":
             return torch.zeros(bs, 21, device=clip.device)
         return self.au_head.logits21_(fused, bs)
+
+    def _forward_train(self, clip, audio):
+        """Same data flow with autograd-visible regions (autograd.py); frozen sub-models (requires_grad=False everywhere,
+        inputs without grad) still take the inference kernels inside their modules."""
+        bs = clip.shape[0]
+        vm = self.video_model.video_model
+        a_feat = self.audio_model.audio_model(audio)
+        tok_a = self._au_tokens(self.audio_model.au_head, a_feat, bs)
+        cls = vm.t_former(vm.s_former(clip[:, -vm.num_channels:].permute(0, 2, 1, 3, 4)))
+        tok_v = self._au_tokens(self.video_model.au_head, cls, bs)
+        fused = torch.cat([tok_a, tok_v], dim=1)                      # [B*12, 256]: audio | video (models/avformer.py:100)
+        if self.task != "AU":
+            return torch.zeros(bs, 21, device=clip.device)
+        return self.au_head.logits21_train(fused, bs)
+
+    @staticmethod
+    def _au_tokens(head, emb, bs):
+        if needs_grad(head, emb):
+            return head.tokens_train(emb, bs)
+        emb = emb.detach().float().contiguous()
+        return head.tokens_into(emb, emb.shape[1], bs)
+
+    def hot_path_train(self, stage3, frame_feat, audio_feat):
+        """hot_path() with autograd: returns (sformer_out, out21); call .backward() on a loss of either."""
+        vm = self.video_model.video_model
+        s_out = vm.s_former.sformer(stage3)
+        n_clips = frame_feat.numel() // (vm.t_former.num_patches * vm.t_former.dim)
+        cls = vm.t_former(frame_feat)
+        tok_v = self._au_tokens(self.video_model.au_head, cls, n_clips)
+        tok_a = self._au_tokens(self.audio_model.au_head, audio_feat, n_clips)
+        return s_out, self.au_head.logits21_train(torch.cat([tok_a, tok_v], dim=1), n_clips)
+
+    def set_dropout(self, p: float):
+        """Override the dropout rate of every encoder stack (the reference uses 0.2 in the audio AU_former and the fusion head)."""
+        for m in self.modules():
+            if isinstance(m, Transformer):
+                m.dropout = float(p)
+        return self
 
     def hot_path(self, stage3, frame_feat, audio_feat, want_decisions=False):
         """The transformer stack alone, on tensors already at its boundaries (what bench.py times and

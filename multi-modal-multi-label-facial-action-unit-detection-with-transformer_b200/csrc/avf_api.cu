@@ -210,7 +210,7 @@ int avf_attention_fwd(int io_mode, const void* qkv, void* out, int32_t n_seq, in
 int avf_sformer_tokens_pack(int io_mode, const void* fmap, const float* pos, float* x, int32_t n_frames, int32_t dim, int32_t hw, void* stream) {
   int e = require_device();
   if (e) return e;
-  AVF_REQUIRE(fmap && pos && x, AVF_EINVAL, "sformer_tokens_pack: null pointer");
+  AVF_REQUIRE(fmap && x, AVF_EINVAL, "sformer_tokens_pack: null pointer");      // pos == NULL: plain transpose (backward of unpack)
   return sformer_pack(io_mode, fmap, pos, x, n_frames, dim, hw, static_cast<cudaStream_t>(stream));
 }
 

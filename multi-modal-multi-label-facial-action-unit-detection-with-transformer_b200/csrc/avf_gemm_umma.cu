@@ -8,8 +8,17 @@
 // overlaps the other's main loop.
 //
 // Replaces the cuBLAS calls behind nn.Linear at models/heads.py:192,195,212,215 of the reference.
+//
+// Training adds two operand orientations without any transposed copy in HBM (tools/umma_probe.cu T7-T9 pin the
+// descriptors on hardware): an operand stored with the reduction index as its ROW index ([K, M] or [K, N] row-major) is
+// fetched as 64x64 boxes and described to tcgen05.mma as MN-major SW128 (LBO = 8192 B between 64-wide panels,
+// SBO = 1024 B between 8-row groups, +2048 B per UMMA_K).  That gives
+//   dgrad  dX[R,Kin]  = dY[R,Nout] * W[Nout,Kin]        A K-major, B = W itself MN-major
+//   wgrad  dW[Nout,Kin] = dY[R,Nout]^T * X[R,Kin]       A and B both MN-major, reduction over the token rows R,
+// the latter split along R over CTAs (deterministic partial tiles + a reduction kernel).
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "avf_common.cuh"
@@ -35,15 +44,41 @@ struct GemmCfg {
 // Epilogue math on one 32-column chunk held in registers, then the store of that chunk.
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
-                                               const float* __restrict__ bias, const float* res, int ld_res, int flags) {
+                                               const float* __restrict__ bias, const float* res, int ld_res, int flags,
+                                               __nv_bfloat16* aux, int ld_aux) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (flags & AVF_EPI_DGELU) {       // backward of the tanh-GELU: multiply by gelu'(pre-activation)
+    const __nv_bfloat16* ap = aux + size_t(row) * ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(ap + j);
+      const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        f[j + 2 * q] *= gelu_tanh_grad(__uint_as_float(w[q] << 16));
+        f[j + 2 * q + 1] *= gelu_tanh_grad(__uint_as_float(w[q] & 0xffff0000u));
+      }
+    }
+  }
   if (flags & AVF_EPI_BIAS) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
       f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if (flags & AVF_EPI_SAVE_PRE) {    // training forward: keep the pre-activation (bf16) for the GELU backward
+    __nv_bfloat16* ap = aux + size_t(row) * ld_aux + col0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o;
+      o.x = pack_bf16x2(f[j], f[j + 1]);
+      o.y = pack_bf16x2(f[j + 2], f[j + 3]);
+      o.z = pack_bf16x2(f[j + 4], f[j + 5]);
+      o.w = pack_bf16x2(f[j + 6], f[j + 7]);
+      *reinterpret_cast<uint4*>(ap + j) = o;
     }
   }
   if (flags & AVF_EPI_GELU) {
@@ -79,11 +114,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // (n-block fastest, so CTAs that run concurrently share the A tile in L2).  The TMEM accumulator is double
 // buffered (2 x BN columns): the MMA warp fills buffer (t+1)&1 while the 8 epilogue warps drain buffer t&1.
-template <int BN, int STAGES, typename OutT>
+template <int BN, int STAGES, typename OutT, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  OutT* C, int ldc, const float* __restrict__ bias,
-                 const float* res, int ld_res, int M, int N, int K, int flags) {
+                 const float* res, int ld_res, int M, int N, int K, int flags,
+                 __nv_bfloat16* aux, int ld_aux, int splits, size_t split_stride) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,9 +130,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks = K / BK;
+  const int kblocks_total = (K + BK - 1) / BK;     // a ragged last block is zero-filled by TMA
+  const int kb_per_split = (kblocks_total + splits - 1) / splits;
   const int n_blocks = N / BN;
-  const int n_tiles = n_blocks * ((M + BM - 1) / BM);
+  const int mn_tiles = n_blocks * ((M + BM - 1) / BM);
+  const int n_tiles = mn_tiles * splits;           // tile = split * mn_tiles + (m_blk * n_blocks + n_blk)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -124,39 +162,54 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+        const int m0 = (mn / n_blocks) * BM, n0 = (mn % n_blocks) * BN;
+        const int kb0 = split * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
-          tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int p = 0; p < BM / 64; ++p) tma_load_2d(st + p * 8192, &tm_a, &full_bar[s], m0 + p * 64, kb * BK);
+          } else {
+            tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int p = 0; p < BN / 64; ++p) tma_load_2d(st + Cfg::A_BYTES + p * 8192, &tm_w, &full_bar[s], n0 + p * 64, kb * BK);
+          } else {
+            tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait(&acc_empty[buf], aph ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int split = tile / mn_tiles;
+        const int kb0 = split * kb_per_split, kb1 = min(kblocks_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint64_t da = make_desc_sw128_kmajor(a_addr);
-          const uint64_t db = make_desc_sw128_kmajor(a_addr + Cfg::A_BYTES);
+          // K-major: +32 bytes per UMMA_K inside the 128B swizzle span.  MN-major: 16 K-rows of 128 B = +2048 bytes,
+          // panels of 64 MN elements 8192 B apart (LBO), 8-row groups 1024 B apart (SBO).
+          const uint64_t da = A_MN ? make_desc(a_addr, 8192, 1024, 2) : make_desc_sw128_kmajor(a_addr);
+          const uint64_t db = B_MN ? make_desc(a_addr + Cfg::A_BYTES, 8192, 1024, 2) : make_desc_sw128_kmajor(a_addr + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance along K inside the 128B swizzle span: +32 bytes per UMMA_K (>>4 in descriptor units)
-            umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da + uint64_t(k * (A_MN ? 128 : 2)), db + uint64_t(k * (B_MN ? 128 : 2)), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs have read it
         }
@@ -169,7 +222,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     constexpr int HALF_COLS = BN / 2;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
+      const int m0 = (mn / n_blocks) * BM, n0 = (mn % n_blocks) * BN;
+      OutT* Cs = C + size_t(split) * split_stride;
       const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&acc_full[buf], aph);
@@ -185,7 +240,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, C, ldc, bias, res, ld_res, flags);
+        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux);
       }
     }
   }
@@ -244,52 +299,122 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, typename OutT>
-static int launch_gemm(const void* a, int lda, const void* w, OutT* c, int ldc, const float* bias,
-                       const float* res, int ld_res, int m, int n, int k, int flags, cudaStream_t stream) {
+template <int BN, int STAGES, typename OutT, bool A_MN, bool B_MN>
+static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, int ldc, const float* bias,
+                       const float* res, int ld_res, int m, int n, int k, int flags, const void* aux, int ld_aux,
+                       int splits, size_t split_stride, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, STAGES>;
   CUtensorMap ta, tw;
-  int e = make_tmap_bf16_2d(&ta, a, m, k, lda, BM);
+  // K-major operand: [rows = M|N, cols = K], box 64 x {128|BN}.  MN-major operand: [rows = K, cols = M|N], box 64 x 64.
+  int e = A_MN ? make_tmap_bf16_2d(&ta, a, k, m, lda, 64) : make_tmap_bf16_2d(&ta, a, m, k, lda, BM);
   if (e) return e;
-  e = make_tmap_bf16_2d(&tw, w, n, k, k, BN);
+  e = B_MN ? make_tmap_bf16_2d(&tw, w, k, n, ldw, 64) : make_tmap_bf16_2d(&tw, w, n, k, ldw, BN);
   if (e) return e;
-  auto kern = gemm_umma_kernel<BN, STAGES, OutT>;
+  auto kern = gemm_umma_kernel<BN, STAGES, OutT, A_MN, B_MN>;
   static bool configured = false;
   if (!configured) {
     AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int n_tiles = (n / BN) * ceil_div(m, BM);
-  kern<<<min(n_tiles, sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags);
+  const int n_tiles = (n / BN) * ceil_div(m, BM) * splits;
+  kern<<<min(n_tiles, sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
+                                                                   static_cast<__nv_bfloat16*>(const_cast<void*>(aux)), ld_aux, splits, split_stride);
   AVF_LAUNCH_CHECK("gemm_umma_kernel");
   return 0;
+}
+
+namespace {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out) {
+  const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(part + size_t(s) * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+}  // namespace
+
+// General bf16 GEMM  C[M,N] = epi(op(A) op(B)), fp32 accumulation in TMEM.
+//   trans_a = 0: A is [M,K] row-major (lda);  1: A is stored [K,M] row-major (reduction index = row).
+//   trans_b = 0: B is [N,K] row-major (nn.Linear layout, C = A B^T);  1: B is stored [K,N] row-major.
+// When both operands are MN-major (wgrad: K = token rows) the reduction is split over CTAs; `ws` then receives the
+// partial tiles and a second kernel reduces them in a fixed order (bit-reproducible).
+int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, int ldw, const float* bias, const float* res,
+              int ld_res, const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags,
+              void* ws, size_t ws_bytes, cudaStream_t stream) {
+  AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
+  AVF_REQUIRE(n % 64 == 0, AVF_EUNSUPPORTED, "linear(bf16): N=%d must be a multiple of 64", n);
+  AVF_REQUIRE(trans_a || trans_b || k % 8 == 0, AVF_EUNSUPPORTED, "linear(bf16): K=%d must be a multiple of 8", k);
+  AVF_REQUIRE(!trans_a || m % 64 == 0, AVF_EUNSUPPORTED, "linear(bf16): M=%d of a transposed A must be a multiple of 64", m);
+  AVF_REQUIRE(ldc % 8 == 0 && (!(flags & AVF_EPI_RESIDUAL) || ld_res % 4 == 0), AVF_EINVAL,
+              "linear(bf16): ldc=%d / ld_res=%d break vector alignment", ldc, ld_res);
+  AVF_REQUIRE(!(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) || (aux != nullptr && ld_aux % 8 == 0), AVF_EINVAL,
+              "linear(bf16): DGELU / SAVE_PRE epilogues need the pre-activation buffer");
+  const int m_tiles = ceil_div(m, BM), sms = sm_count();
+  if (trans_a && trans_b) {
+    // wgrad: few output tiles, long reduction -> split K so that every SM has a tile
+    AVF_REQUIRE(c_mode == AVF_FP32 && flags == 0, AVF_EUNSUPPORTED, "linear(bf16): the TN form writes plain fp32");
+    const int bn = n % 128 == 0 ? 128 : 64;
+    const int mn_tiles = m_tiles * (n / bn), kblocks = ceil_div(k, BK);
+    int splits = std::max(1, std::min(kblocks, sms / std::max(1, mn_tiles)));
+    const int per = ceil_div(kblocks, splits);
+    splits = ceil_div(kblocks, per);
+    const size_t elems = size_t(m) * n;
+    float* out = static_cast<float*>(c);
+    float* part = out;
+    size_t stride = 0;
+    if (splits > 1) {
+      AVF_REQUIRE(ldc == n, AVF_EINVAL, "linear(bf16): split-K output must be dense (ldc=%d n=%d)", ldc, n);
+      AVF_REQUIRE(ws != nullptr && ws_bytes >= elems * splits * sizeof(float), AVF_EWORKSPACE,
+                  "linear(bf16): split-K workspace too small: %zu < %zu bytes", ws_bytes, elems * splits * sizeof(float));
+      part = static_cast<float*>(ws);
+      stride = elems;
+    }
+    int e = bn == 128 ? launch_gemm<128, 6, float, true, true>(a, lda, w, ldw, part, ldc, nullptr, nullptr, 0, m, n, k, 0, nullptr, 0, splits, stride, stream)
+                      : launch_gemm<64, 8, float, true, true>(a, lda, w, ldw, part, ldc, nullptr, nullptr, 0, m, n, k, 0, nullptr, 0, splits, stride, stream);
+    if (e) return e;
+    if (splits > 1) {
+      splitk_reduce_kernel<<<unsigned((elems / 4 + 255) / 256), 256, 0, stream>>>(part, splits, elems, out);
+      AVF_LAUNCH_CHECK("splitk_reduce_kernel");
+    }
+    return 0;
+  }
+  AVF_REQUIRE(!trans_a, AVF_EUNSUPPORTED, "linear(bf16): transposed A is only implemented together with transposed B");
+  // widest tile that still gives every SM at least two tiles; small problems get narrower tiles for parallelism
+  int bn = 64;
+  if (n % 256 == 0 && m_tiles * (n / 256) >= 2 * sms) bn = 256;
+  else if (n % 128 == 0 && m_tiles * (n / 128) >= sms) bn = 128;
+  else if (n % 128 == 0 && n / 128 * m_tiles >= sms / 2 && n >= 512) bn = 128;
+#define AVF_GEMM(BN_, ST_, BMN_)                                                                                                   \
+  if (bn == BN_ && bool(trans_b) == BMN_) {                                                                                        \
+    if (c_mode == AVF_BF16)                                                                                                        \
+      return launch_gemm<BN_, ST_, __nv_bfloat16, false, BMN_>(a, lda, w, ldw, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream); \
+    return launch_gemm<BN_, ST_, float, false, BMN_>(a, lda, w, ldw, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream);          \
+  }
+  AVF_GEMM(256, 4, false)
+  AVF_GEMM(128, 6, false)
+  AVF_GEMM(64, 8, false)
+  AVF_GEMM(256, 4, true)
+  AVF_GEMM(128, 6, true)
+  AVF_GEMM(64, 8, true)
+#undef AVF_GEMM
+  return AVF_EUNSUPPORTED;
+}
+
+size_t gemm_umma_workspace_bytes(int m, int n, int k) {       // for the TN (wgrad) form
+  const int sms = sm_count(), bn = n % 128 == 0 ? 128 : 64;
+  const int mn_tiles = ceil_div(m, BM) * (n / bn), kblocks = ceil_div(k, BK);
+  const int splits = std::max(1, std::min(kblocks, sms / std::max(1, mn_tiles)));
+  return splits > 1 ? size_t(m) * n * splits * sizeof(float) : 0;
 }
 
 // C = epi(A W^T) with bf16 operands; c_mode selects fp32 / bf16 output.
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c,
                 int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t stream) {
-  AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
   AVF_REQUIRE(k % BK == 0, AVF_EUNSUPPORTED, "linear(bf16): K=%d must be a multiple of %d", k, BK);
-  AVF_REQUIRE(n % 64 == 0, AVF_EUNSUPPORTED, "linear(bf16): N=%d must be a multiple of 64", n);
-  AVF_REQUIRE(ldc % 8 == 0 && (!(flags & AVF_EPI_RESIDUAL) || ld_res % 4 == 0), AVF_EINVAL,
-              "linear(bf16): ldc=%d / ld_res=%d break vector alignment", ldc, ld_res);
-  // widest tile that still gives every SM at least two tiles; small problems get narrower tiles for parallelism
-  const int m_tiles = ceil_div(m, BM), sms = sm_count();
-  int bn = 64;
-  if (n % 256 == 0 && m_tiles * (n / 256) >= 2 * sms) bn = 256;
-  else if (n % 128 == 0 && m_tiles * (n / 128) >= sms) bn = 128;
-  else if (n % 128 == 0 && n / 128 * m_tiles >= sms / 2 && n >= 512) bn = 128;
-#define AVF_GEMM(BN_, ST_)                                                                                                         \
-  if (bn == BN_) {                                                                                                                 \
-    if (c_mode == AVF_BF16)                                                                                                        \
-      return launch_gemm<BN_, ST_, __nv_bfloat16>(a, lda, w, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream); \
-    return launch_gemm<BN_, ST_, float>(a, lda, w, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, stream);          \
-  }
-  AVF_GEMM(256, 4)
-  AVF_GEMM(128, 6)
-  AVF_GEMM(64, 8)
-#undef AVF_GEMM
-  return AVF_EUNSUPPORTED;
+  return gemm_umma(0, 0, a, lda, w, k, bias, res, ld_res, nullptr, 0, c, ldc, c_mode, m, n, k, flags, nullptr, 0, stream);
 }
 
 }  // namespace avf

@@ -26,6 +26,25 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
                int c_mode, int m, int n, int k, int flags, cudaStream_t st);
 int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
+int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, int ldw, const float* bias, const float* res, int ld_res,
+             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st);
+
+// avf_train.cu
+size_t colsum_workspace_bytes(int rows, int cols);
+int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out, float beta, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t layernorm_bwd_workspace_bytes(int rows, int dim);
+int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, float* dgamma,
+                  float* dbeta, float* dbias, float beta_acc, int rows, int dim, void* ws, size_t ws_bytes, cudaStream_t st);
+int attention_bwd(int io_mode, const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+int au_logits_bwd(const float* dl, int ld_dl, const float* x, int ld_x, const float* w_last, float* dx, int ld_dx, float* dw, int n_clips,
+                  int dim, cudaStream_t st);
+int bn_train_fwd(int out_mode, const float* x, int ld_x, const float* g, const float* b, float* run_mean, float* run_var, float momentum,
+                 void* y, float* save_mean, float* save_rstd, int rows, int dim, cudaStream_t st);
+int bn_bwd(const float* x, int ld_x, const float* dy, const float* g, const float* mean, const float* rstd_or_var, int batch_stats, float* dx,
+           int ld_dx, float* dgamma, float* dbeta, int rows, int dim, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, void* shadow, size_t n, float lr, float b1, float b2, float eps, float wd, int step,
+              int decoupled, float grad_scale, cudaStream_t st);
+
 // avf_attention_mma.cu
 int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
@@ -36,6 +55,10 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
                   const float* pos, cudaStream_t st);
 
 // avf_gemm_umma.cu
+int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, int ldw, const float* bias, const float* res, int ld_res,
+              const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, void* ws, size_t ws_bytes,
+              cudaStream_t stream);
+size_t gemm_umma_workspace_bytes(int m, int n, int k);
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
                 int c_mode, int m, int n, int k, int flags, cudaStream_t st);
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) sformer_pack_kernel(const InT* __restrict
   float* dst = x + size_t(f) * hw * dim;
   for (int i = threadIdx.x; i < dim * hw; i += blockDim.x) {
     const int t = i / dim, c = i - t * dim;
-    dst[i] = tile[c * pitch + t] + __ldg(pos + i);
+    dst[i] = tile[c * pitch + t] + (pos != nullptr ? __ldg(pos + i) : 0.f);
   }
 }
 

@@ -58,6 +58,60 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 }
 
 
+// Same tile shape with arbitrary operand orientation (training, parity mode): element (m,k) of A sits at
+// A[m*a_rs + k*a_cs], element (n,k) of W at W[n*w_rs + k*w_cs].  Scalar loads: this is the fp32 checking path.
+template <typename OutT>
+__global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __restrict__ A, long a_rs, long a_cs, const float* __restrict__ W,
+                                                               long w_rs, long w_cs, OutT* __restrict__ C, int ldc,
+                                                               const float* __restrict__ bias, const float* __restrict__ res, int ld_res,
+                                                               float* aux, int ld_aux, int M, int N, int K, int flags) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      // make the contiguous index the fast one so that loads coalesce in either orientation
+      const int kk_a = a_cs == 1 ? idx & 15 : idx >> 6, mm = a_cs == 1 ? idx >> 4 : idx & 63;
+      const int kk_w = w_cs == 1 ? idx & 15 : idx >> 6, nn = w_cs == 1 ? idx >> 4 : idx & 63;
+      As[kk_a][mm] = (m0 + mm < M && k0 + kk_a < K) ? A[(m0 + mm) * a_rs + (k0 + kk_a) * a_cs] : 0.f;
+      Ws[kk_w][nn] = (n0 + nn < N && k0 + kk_w < K) ? W[(n0 + nn) * w_rs + (k0 + kk_w) * w_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      float v = acc[i][j];
+      if (flags & AVF_EPI_DGELU) v *= gelu_tanh_grad(aux[size_t(r) * ld_aux + c]);
+      if (flags & AVF_EPI_BIAS) v += bias[c];
+      if (flags & AVF_EPI_SAVE_PRE) aux[size_t(r) * ld_aux + c] = v;
+      if (flags & AVF_EPI_GELU) v = gelu_tanh<false>(v);
+      if (flags & AVF_EPI_RESIDUAL) v += res[size_t(r) * ld_res + c];
+      C[size_t(r) * ldc + c] = from_f32<OutT>(v);
+    }
+  }
+}
+
 // 16-byte vectorised row-fragment load (global or shared) with conversion to fp32.
 template <typename T, int N>
 __device__ __forceinline__ void load_frag(const T* __restrict__ p, float (&dst)[N]) {
@@ -172,6 +226,22 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
   if (c_mode == AVF_BF16) gemm_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, lda, w, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags);
   else gemm_f32_kernel<float><<<grid, 256, 0, st>>>(a, lda, w, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags);
   AVF_LAUNCH_CHECK("gemm_f32_kernel");
+  return 0;
+}
+
+int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, int ldw, const float* bias, const float* res, int ld_res,
+             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st) {
+  AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
+  AVF_REQUIRE(!(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) || aux != nullptr, AVF_EINVAL, "linear(fp32): DGELU / SAVE_PRE epilogues need the pre-activation buffer");
+  if (!trans_a && !trans_b && ldw == k && !(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) && k % 16 == 0 && lda % 4 == 0)
+    return linear_f32(a, lda, w, bias, res, ld_res, c, ldc, c_mode, m, n, k, flags, st);
+  dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
+  const long a_rs = trans_a ? 1 : lda, a_cs = trans_a ? lda : 1, w_rs = trans_b ? 1 : ldw, w_cs = trans_b ? ldw : 1;
+  if (c_mode == AVF_BF16)
+    gemm_f32_generic_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags);
+  else
+    gemm_f32_generic_kernel<float><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<float*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags);
+  AVF_LAUNCH_CHECK("gemm_f32_generic_kernel");
   return 0;
 }
 

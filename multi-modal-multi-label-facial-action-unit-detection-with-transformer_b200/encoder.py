@@ -35,12 +35,12 @@ def default_precision() -> str:
     return _DEFAULT_PRECISION
 
 
-def _check_inference(module: nn.Module, x: torch.Tensor) -> None:
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
-        if not getattr(module, "_avf_allow_no_grad_path", False):
-            raise NotImplementedError(
-                "avformer_b200: this build runs the encoder forward only; call it under torch.no_grad() "
-                "(the backward kernels are not part of this milestone)")
+def needs_grad(module: nn.Module, *inputs: torch.Tensor) -> bool:
+    """True when autograd has to see this call: grad mode on and an input or a parameter of ``module`` requires grad.
+    Such calls take the tape-keeping path (autograd.py); everything else takes the inference kernels."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(t is not None and t.requires_grad for t in inputs) or any(p.requires_grad for p in module.parameters())
 
 
 class GELU(nn.Module):
@@ -144,18 +144,33 @@ class Transformer(nn.Module):
     def shape(self, n_seq: int, n_tok: int):
         return AF.make_shape(n_seq, n_tok, self.dim, self.heads, self.dim_head, self.mlp_dim, self.depth)
 
+    def param_list(self):
+        """Parameters in avf_layer_weights order, layer by layer (the order autograd.EncoderStackFn returns gradients in)."""
+        names = [n for n, _ in AF.LayerWeights._fields_]
+        return [lw[n] for lw in self._layer_tensors() for n in names]
+
+    def _check_dropout(self):
+        if self.training and self.dropout > 0.0:
+            raise NotImplementedError("avformer_b200: dropout>0 in train() mode is not implemented; set_dropout(0.0) or eval()")
+
     # -- forward -------------------------------------------------------------------------------
     def forward_(self, x2d: torch.Tensor, n_seq: int, n_tok: int, out: Optional[torch.Tensor] = None, ld_out: int = 0) -> torch.Tensor:
-        """In place on an fp32 residual stream [n_seq*n_tok, dim]."""
-        if self.training and self.dropout > 0.0:
-            raise NotImplementedError("avformer_b200: dropout>0 in train() mode is not implemented (eval() or dropout=0)")
+        """Inference kernels, in place on an fp32 residual stream [n_seq*n_tok, dim]."""
+        self._check_dropout()
         return AF.encoder_stack_fwd_(x2d, self.packed(), self.shape(n_seq, n_tok), out, ld_out)
+
+    def forward_train(self, x2d: torch.Tensor, n_seq: int, n_tok: int) -> torch.Tensor:
+        """Autograd-visible forward on an fp32 token matrix [n_seq*n_tok, dim] (activation tape kept for backward)."""
+        from .autograd import EncoderStackFn
+        self._check_dropout()
+        return EncoderStackFn.apply(x2d, self, n_seq, n_tok, *self.param_list())
 
     def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:
         if mask is not None:
             raise NotImplementedError("attention masks are never passed on the AVFormer path (models/heads.py:225-232 is dead code)")
-        _check_inference(self, x)
         AF._cuda(x, "x")
         b, n, d = x.shape
+        if needs_grad(self, x):
+            return self.forward_train(x.reshape(b * n, d), b, n).view(b, n, d)
         y = x.detach().float().reshape(b * n, d).clone()
         return self.forward_(y, b, n).view(b, n, d)

@@ -107,9 +107,10 @@ class PackedStack:
                 self.keep.append(t)
                 setattr(self.array[i], name, t.data_ptr())
         self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.epoch = WEIGHTS_EPOCH
 
     def stale(self) -> bool:
-        return any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -261,3 +262,172 @@ def set_fused_enabled(enabled: bool) -> bool:
 
 def encoder_fused_supported(shape: StackShape, precision="bf16") -> bool:
     return bool(_lib.lib().avf_encoder_fused_supported(ctypes.byref(shape), _mode(precision)))
+
+
+# ------------------------------------------------------------------------------------------------
+# training: tape forward, backward, optimiser (include/avformer_b200.h, section "training")
+# ------------------------------------------------------------------------------------------------
+WEIGHTS_EPOCH = 0          # bumped by optimisers that update parameters through raw pointers (optim.FusedAdam)
+
+
+def bump_weights_epoch() -> None:
+    """Tell every packed (bf16 / stacked) weight copy that the fp32 master parameters changed underneath it."""
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
+def _act_dtype(mode: int) -> torch.dtype:
+    return torch.bfloat16 if mode == AVF_BF16 else torch.float32
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False, m: Optional[int] = None, n: Optional[int] = None,
+         k: Optional[int] = None, bias=None, residual=None, aux=None, flags: int = 0, out_dtype=torch.float32, precision="bf16") -> torch.Tensor:
+    """C[M,N] = epi(op(A) op(B)) — see avf_gemm.  a / b are 2-D contiguous; trans_* say the reduction index is the ROW index."""
+    mode = _mode(precision)
+    _cuda(a, "a")
+    a, b = a.contiguous(), b.contiguous()
+    m = m if m is not None else (a.shape[1] if trans_a else a.shape[0])
+    k = k if k is not None else (a.shape[0] if trans_a else a.shape[1])
+    n = n if n is not None else (b.shape[1] if trans_b else b.shape[0])
+    c = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    L = _lib.lib()
+    need = L.avf_gemm_workspace_bytes(mode, int(trans_a), int(trans_b), m, n, k)
+    ws = workspace(max(need, 256), a.device)
+    check(L.avf_gemm(mode, int(trans_a), int(trans_b), _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(bias), _ptr(residual),
+                     residual.stride(0) if residual is not None else 0, _ptr(aux), aux.stride(0) if aux is not None else 0, _ptr(c), n,
+                     _io_mode(c), m, n, k, flags, _ptr(ws), ws.numel(), _stream()), "gemm")
+    return c
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D fp32 / bf16 matrix (unit column stride) -> fp32 [cols]."""
+    _cuda(x, "x")
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    ws = workspace(L.avf_colsum_workspace_bytes(rows, cols), x.device)
+    check(L.avf_colsum(_io_mode(x), _ptr(x), x.stride(0), rows, cols, _ptr(out), _ptr(ws), ws.numel(), _stream()), "colsum")
+    return out
+
+
+def layernorm_bwd_(x: torch.Tensor, gamma: torch.Tensor, dy_norm: torch.Tensor, dres: torch.Tensor, want_bf16: bool = False):
+    """In place on dres [rows, dim] (fp32): dres += LN'(dy_norm).  Returns (dres, dx_bf16|None, dgamma, dbeta, dbias)."""
+    rows, dim = dres.shape
+    dev = dres.device
+    dg, db, dbias = (torch.empty(dim, dtype=torch.float32, device=dev) for _ in range(3))
+    xb = torch.empty((rows, dim), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    L = _lib.lib()
+    ws = workspace(L.avf_layernorm_bwd_workspace_bytes(rows, dim), dev)
+    check(L.avf_layernorm_bwd(_ptr(x), x.stride(0), _ptr(_f32c(gamma)), _ptr(dy_norm), _ptr(dres), dres.stride(0), _ptr(xb), _ptr(dg), _ptr(db),
+                              _ptr(dbias), rows, dim, _ptr(ws), ws.numel(), _stream()), "layernorm_bwd")
+    return dres, xb, dg, db, dbias
+
+
+def attention_bwd(qkv: torch.Tensor, dout: torch.Tensor, n_seq: int, n_tok: int, heads: int, dim_head: int) -> torch.Tensor:
+    qkv, dout = _cuda(qkv, "qkv").contiguous(), dout.contiguous()
+    dqkv = torch.empty_like(qkv)
+    check(_lib.lib().avf_attention_bwd(_io_mode(qkv), _ptr(qkv), _ptr(dout), _ptr(dqkv), n_seq, n_tok, heads, dim_head, _stream()), "attention_bwd")
+    return dqkv
+
+
+def encoder_stack_fwd_train(x: torch.Tensor, packed: PackedStack, shape: StackShape):
+    """Forward of a whole stack that keeps the activations the backward needs.  x [n_seq*n_tok, dim] fp32 is left
+    untouched; returns (y, tape)."""
+    _cuda(x, "x")
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise TypeError("encoder_stack_fwd_train: x must be a float32 residual stream with unit column stride")
+    L = _lib.lib()
+    tape = torch.empty(L.avf_encoder_tape_bytes(ctypes.byref(shape), packed.mode), dtype=torch.uint8, device=x.device)
+    y = torch.empty((x.shape[0], shape.dim), dtype=torch.float32, device=x.device)
+    check(L.avf_encoder_stack_fwd_train(packed.mode, ctypes.byref(shape), packed.array, _ptr(x), x.stride(0), _ptr(y), shape.dim, _ptr(tape),
+                                        tape.numel(), _stream()), "encoder_stack_fwd_train")
+    return y, tape
+
+
+def encoder_stack_bwd_(dx: torch.Tensor, packed: PackedStack, shape: StackShape, tape: torch.Tensor, want: Sequence[bool]):
+    """dx [rows, dim] fp32 dense: dL/dy on entry, dL/dx on return.  ``want`` has 11*depth flags in avf_layer_weights
+    order; returns the matching list of fp32 gradient tensors (None where not wanted)."""
+    from ._lib import LayerGrads
+    names = [n for n, _ in LayerWeights._fields_]
+    grads: List[Optional[torch.Tensor]] = []
+    arr = (LayerGrads * packed.depth)()
+    for l in range(packed.depth):
+        for j, name in enumerate(names):
+            src = packed.sources[l * len(names) + j]
+            g = torch.empty(src.shape, dtype=torch.float32, device=dx.device) if want[l * len(names) + j] else None
+            grads.append(g)
+            setattr(arr[l], name, g.data_ptr() if g is not None else None)
+    L = _lib.lib()
+    ws = workspace(L.avf_encoder_bwd_workspace_bytes(ctypes.byref(shape), packed.mode), dx.device)
+    check(L.avf_encoder_stack_bwd(packed.mode, ctypes.byref(shape), packed.array, _ptr(tape), tape.numel(), _ptr(dx), dx.stride(0), arr, _ptr(ws),
+                                  ws.numel(), _stream()), "encoder_stack_bwd")
+    return dx, grads
+
+
+def sformer_tokens_pack(fmap: torch.Tensor, pos: Optional[torch.Tensor]) -> torch.Tensor:
+    """[F,C,H,W] -> fp32 tokens [F*H*W, C] (+ pos [H*W, C]); pos=None is the plain transpose."""
+    fmap = _cuda(fmap, "fmap").contiguous()
+    F_, C, H, W = fmap.shape
+    x = torch.empty((F_ * H * W, C), dtype=torch.float32, device=fmap.device)
+    check(_lib.lib().avf_sformer_tokens_pack(_io_mode(fmap), _ptr(fmap), _ptr(_f32c(pos)) if pos is not None else None, _ptr(x), F_, C, H * W,
+                                             _stream()), "sformer_tokens_pack")
+    return x
+
+
+def sformer_tokens_unpack(x: torch.Tensor, shape4, dtype: torch.dtype) -> torch.Tensor:
+    F_, C, H, W = shape4
+    fmap = torch.empty((F_, C, H, W), dtype=dtype, device=x.device)
+    check(_lib.lib().avf_sformer_tokens_unpack(_io_mode(fmap), _ptr(x), _ptr(fmap), F_, C, H * W, _stream()), "sformer_tokens_unpack")
+    return fmap
+
+
+def au_former_front_train(emb: torch.Tensor, n_clips: int, bn_w, bn_b, run_mean, run_var, batch_stats: bool, momentum: float,
+                          w_cat: torch.Tensor, b_cat: torch.Tensor, pos: torch.Tensor, mode: int):
+    """BN (batch or running statistics) + 12 stacked projections + pos, keeping what the backward needs.
+    emb [n_clips, in_dim] fp32 with unit column stride (any row stride).  Returns (tokens [n_clips*12, emb_dim], tape)."""
+    _cuda(emb, "emb")
+    in_dim, emb_dim = w_cat.shape[1], w_cat.shape[0] // 12
+    L = _lib.lib()
+    tape = torch.empty(L.avf_au_former_front_tape_bytes(mode, n_clips, in_dim), dtype=torch.uint8, device=emb.device)
+    x = torch.empty((n_clips * 12, emb_dim), dtype=torch.float32, device=emb.device)
+    check(L.avf_au_former_front_fwd_train(mode, _ptr(emb), emb.stride(0), _ptr(_f32c(bn_w)), _ptr(_f32c(bn_b)), _ptr(run_mean), _ptr(run_var),
+                                          int(batch_stats), float(momentum), _ptr(w_cat), _ptr(b_cat), _ptr(_f32c(pos)), _ptr(x), n_clips, in_dim,
+                                          emb_dim, _ptr(tape), tape.numel(), _stream()), "au_former_front_fwd_train")
+    return x, tape
+
+
+def au_former_front_bwd(emb: torch.Tensor, n_clips: int, bn_w, run_mean, run_var, batch_stats: bool, w_cat: torch.Tensor, tape: torch.Tensor,
+                        dx: torch.Tensor, mode: int, want_emb=True, want_bn=True, want_w=True):
+    """-> (demb [n_clips,in_dim] | None, dbn_gamma, dbn_beta | None, dw_cat [12*emb,in] | None, db_cat [12*emb] (== dpos))."""
+    in_dim, emb_dim = w_cat.shape[1], w_cat.shape[0] // 12
+    dev = dx.device
+    dx = dx.contiguous()
+    demb = torch.empty((n_clips, in_dim), dtype=torch.float32, device=dev) if want_emb else None
+    dg = torch.empty(in_dim, dtype=torch.float32, device=dev) if want_bn else None
+    db = torch.empty(in_dim, dtype=torch.float32, device=dev) if want_bn else None
+    dw = torch.empty((12 * emb_dim, in_dim), dtype=torch.float32, device=dev) if want_w else None
+    dbc = torch.empty(12 * emb_dim, dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = workspace(L.avf_au_former_front_bwd_workspace_bytes(mode, n_clips, in_dim, emb_dim), dev)
+    check(L.avf_au_former_front_bwd(mode, _ptr(emb), emb.stride(0), _ptr(_f32c(bn_w)), _ptr(run_mean), _ptr(run_var), int(batch_stats), _ptr(w_cat),
+                                    _ptr(tape), tape.numel(), _ptr(dx), _ptr(demb), in_dim, _ptr(dg), _ptr(db), _ptr(dw), _ptr(dbc), n_clips, in_dim,
+                                    emb_dim, _ptr(ws), ws.numel(), _stream()), "au_former_front_bwd")
+    return demb, dg, db, dw, dbc
+
+
+def au_logits_bwd(dlogits: torch.Tensor, x: torch.Tensor, w_last: torch.Tensor, n_clips: int, want_dx=True, want_dw=True):
+    """dlogits [n_clips, >=12] fp32 (row stride free) -> (dx [n_clips*12, dim] | None, dw_last [12, dim] | None)."""
+    dim = w_last.shape[1]
+    dx = torch.empty((n_clips * 12, dim), dtype=torch.float32, device=x.device) if want_dx else None
+    dw = torch.empty((12, dim), dtype=torch.float32, device=x.device) if want_dw else None
+    check(_lib.lib().avf_au_logits_bwd(_ptr(dlogits), dlogits.stride(0), _ptr(x), x.stride(0), _ptr(w_last), _ptr(dx), dim, _ptr(dw), n_clips, dim,
+                                       _stream()), "au_logits_bwd")
+    return dx, dw
+
+
+def adam_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float, decoupled: bool = False, grad_scale: float = 1.0, shadow: Optional[torch.Tensor] = None) -> None:
+    """One fused Adam / AdamW step over flat fp32 buckets (in place on p, m, v)."""
+    _cuda(p, "params")
+    check(_lib.lib().avf_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(shadow), p.numel(), lr, beta1, beta2, eps, weight_decay, step,
+                                   int(decoupled), grad_scale, _stream()), "adam_step")

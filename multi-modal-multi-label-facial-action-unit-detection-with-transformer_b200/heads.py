@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from . import functional as AF
-from .encoder import Transformer, _check_inference, default_precision
+from .encoder import Transformer, default_precision, needs_grad
 
 
 class _PackedFront:
@@ -23,9 +23,10 @@ class _PackedFront:
         self.w = AF.to_bf16(w) if mode == AF.AVF_BF16 else w
         self.b = torch.cat([l.bias.detach().float() for l in linears], dim=0).contiguous()
         self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.epoch = AF.WEIGHTS_EPOCH
 
     def stale(self):
-        return any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != AF.WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
 
 
 class _PackedLast:
@@ -33,9 +34,10 @@ class _PackedLast:
         self.sources = [l.weight for l in linears]
         self.w = torch.cat([l.weight.detach().float() for l in linears], dim=0).contiguous()     # [12, dim]
         self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.epoch = AF.WEIGHTS_EPOCH
 
     def stale(self):
-        return any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != AF.WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
 
 
 class AU_former(nn.Module):
@@ -71,19 +73,37 @@ class AU_former(nn.Module):
         ld_emb): the cls rows of a TFormer token matrix are consumed in place.  The last layer's result goes
         to ``out`` (row stride ld_out) when given — that is how the audio and video halves of the
         [B,12,256] fusion input get written side by side without a cat (models/avformer.py:100)."""
-        if self.AU_BN1.training:
-            raise NotImplementedError("avformer_b200: AU_BN1 batch statistics (train() mode) are not implemented; use eval()")
         f = self._packed_front()
         bn = self.AU_BN1
-        x = AF.au_former_front(emb, ld_emb, n_clips, (bn.weight, bn.bias, bn.running_mean, bn.running_var), f.w, f.b,
-                               self.pos_embedding[0], f.mode)
+        if bn.training:
+            # train() without gradients (a frozen sub-model inside a training loop): batch statistics, running ones updated
+            view = torch.as_strided(emb, (n_clips, f.w.shape[1]), (ld_emb, 1))
+            x, _ = AF.au_former_front_train(view, n_clips, bn.weight, bn.bias, bn.running_mean, bn.running_var, True,
+                                            0.1 if bn.momentum is None else bn.momentum, f.w, f.b, self.pos_embedding[0], f.mode)
+            bn.num_batches_tracked += 1
+        else:
+            x = AF.au_former_front(emb, ld_emb, n_clips, (bn.weight, bn.bias, bn.running_mean, bn.running_var), f.w, f.b,
+                                   self.pos_embedding[0], f.mode)
         return self.corr_transformer.forward_(x, n_clips, 12, out, ld_out)
 
+    def front_params(self):
+        return [p for i in range(1, 13) for p in (getattr(self, f"AU_linear_p{i}").weight, getattr(self, f"AU_linear_p{i}").bias)]
+
+    def tokens_train(self, emb: torch.Tensor, n_clips: int) -> torch.Tensor:
+        """Autograd-visible version of tokens_into: emb [n_clips, 512] (any row stride) -> tokens [n_clips*12, emb_dim]."""
+        from .autograd import AUFrontFn
+        x = AUFrontFn.apply(emb, self.AU_BN1.weight, self.AU_BN1.bias, self.pos_embedding, self, n_clips, *self.front_params())
+        return self.corr_transformer.forward_train(x, n_clips, 12)
+
     def forward(self, emb):
-        _check_inference(self, emb)
         AF._cuda(emb, "emb")
-        emb = emb.detach().float().contiguous()
         bs = emb.shape[0]
+        if needs_grad(self, emb):
+            tok = self.tokens_train(emb, bs)
+            with torch.no_grad():      # the per-modality AU logits are discarded by the AVFormer (models/avformer.py:53,70): no gradient path
+                au_out = AF.au_logits(tok.detach(), self._packed_last().w, bs)[:, :12]
+            return au_out, tok.view(bs, 12, -1)
+        emb = emb.detach().float().contiguous()
         tok = self.tokens_into(emb, emb.shape[1], bs)
         au_out = AF.au_logits(tok, self._packed_last().w, bs)[:, :12]
         return au_out, tok.view(bs, 12, -1)
@@ -111,10 +131,21 @@ class former_AU_head(nn.Module):
         self.corr_transformer.forward_(tokens2d, n_clips, 12)
         return AF.au_logits(tokens2d, self._packed_last().w, n_clips, want_decisions)
 
+    def last_params(self):
+        return [getattr(self, f"AU_linear_last{i}").weight for i in range(1, 13)]
+
+    def logits21_train(self, tokens2d: torch.Tensor, n_clips: int) -> torch.Tensor:
+        """Autograd-visible version of logits21_ on fp32 tokens [n_clips*12, emb_dim] -> [B,21]."""
+        from .autograd import AddPosFn, AULogitsFn
+        x = AddPosFn.apply(tokens2d, self.pos_embedding, 12)
+        x = self.corr_transformer.forward_train(x, n_clips, 12)
+        return AULogitsFn.apply(x, self, n_clips, *self.last_params())
+
     def forward(self, input):
-        _check_inference(self, input)
         AF._cuda(input, "input")
         bs = input.shape[0]
+        if needs_grad(self, input):
+            return self.logits21_train(input.reshape(bs * 12, -1), bs)[:, :12]
         tok = input.detach().float().reshape(bs * 12, -1).clone()
         return self.logits21_(tok, bs)[:, :12]
 

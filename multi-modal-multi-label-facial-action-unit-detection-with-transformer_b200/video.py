@@ -8,7 +8,7 @@ import torch
 from torch import nn
 
 from . import functional as AF
-from .encoder import Transformer, _check_inference
+from .encoder import Transformer, needs_grad
 
 
 class Dummy(nn.Module):
@@ -94,12 +94,13 @@ class ResFormer(nn.Module):
         n_tok = fmap.shape[2] * fmap.shape[3]
         if n_tok > self.pos_embedding.shape[1]:
             raise ValueError(f"stage-3 map has {n_tok} positions but pos_embedding holds {self.pos_embedding.shape[1]}")
-        if st.training and st.dropout > 0.0:
-            raise NotImplementedError("avformer_b200: dropout>0 in train() mode is not implemented")
+        st._check_dropout()
+        if needs_grad(st, fmap, self.pos_embedding):
+            from .autograd import SFormerFn
+            return SFormerFn.apply(fmap, self.pos_embedding, st, *st.param_list())
         return AF.sformer_fwd(fmap, self.pos_embedding[0, :n_tok], st.packed(), st.heads, st.dim_head, st.mlp_dim)
 
     def forward(self, x):
-        _check_inference(self.spatial_transformer, x)
         b, t, c, h, w = x.shape
         fmap = self.stem_to_stage3(x.contiguous().view(-1, c, h, w))
         fmap = self.sformer(fmap)
@@ -123,13 +124,18 @@ class TFormer(nn.Module):
         if x.numel() % (self.num_patches * self.dim) != 0:
             raise ValueError(f"TFormer(num_patches={self.num_patches}): input of {tuple(x.shape)} is not a whole number of clips")
         n_clips = x.numel() // (self.num_patches * self.dim)
+        if needs_grad(self, x):
+            from .autograd import TFormerEmbedFn
+            tok = TFormerEmbedFn.apply(x, self.cls_token, self.pos_embedding, self.num_patches)
+            return self.spatial_transformer.forward_train(tok, n_clips, self.num_patches + 1), n_clips
         tok = AF.tformer_embed(x.detach(), self.cls_token.view(-1), self.pos_embedding[0], self.num_patches)
         self.spatial_transformer.forward_(tok, n_clips, self.num_patches + 1)
         return tok, n_clips
 
     def forward(self, x):
-        _check_inference(self.spatial_transformer, x)
         tok, n_clips = self.tokens(x)
+        if tok.requires_grad:
+            return tok.view(n_clips, self.num_patches + 1, self.dim)[:, 0]          # cls rows (a view: data movement only)
         return AF.tformer_cls_extract(tok, n_clips, self.num_patches + 1)
 
 

@@ -282,6 +282,66 @@ def hot_path_forward(stage3, frame_feat, audio_feat, p: P, n_frames: int) -> Dic
 
 
 # --------------------------------------------------------------------------
+# Training step of the hot path (train.py:206-236): loss, gradients, Adam
+# --------------------------------------------------------------------------
+def hot_path_forward_train(stage3, frame_feat, audio_feat, p: P, n_frames: int, batch_stats: bool = False) -> Dict[str, torch.Tensor]:
+    """hot_path_forward with the AU_BN1 layers in train() mode when ``batch_stats`` (nn.BatchNorm1d: biased batch
+    variance for normalisation, models/heads.py:263,293)."""
+    out = {"sformer_out": sformer_tokens(stage3, p, "video_model.video_model.s_former.")}
+    out["tformer_cls"] = tformer(frame_feat, p, "video_model.video_model.t_former.", n_frames)
+    _, out["video_tokens"] = au_former(out["tformer_cls"], p, "video_model.au_head.", batch_stats)
+    _, out["audio_tokens"] = au_former(audio_feat, p, "audio_model.au_head.", batch_stats)
+    out["logits"] = fusion_head(torch.cat([out["audio_tokens"], out["video_tokens"]], dim=2), p, "au_head.")
+    return out
+
+
+def hot_path_grads(stage3, frame_feat, audio_feat, labels, p: P, n_frames: int, batch_stats: bool = False, sformer_loss_weight: float = 0.0):
+    """loss.backward() of train.py:235 on the hot path: AULoss of the fusion-head logits (models/avformer.py:114-117)
+    differentiated by torch autograd THROUGH THE RESTATED FORWARD above (the reference does exactly that with its own
+    modules; pinned by tests/golden/grad_T16.npz).  In the full model the SFormer output reaches the loss through conv
+    stage 4; on the isolated hot path a synthetic term  sformer_loss_weight * mean(sformer_out * probe)  stands in for it
+    (probe = a fixed pseudo-random +-1 pattern) so that the SFormer backward is exercised too.
+    Returns (loss, grads by state-dict name, input grads dict)."""
+    q = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in p.items()}
+    ins = {"stage3": stage3.clone().requires_grad_(True), "frame_feat": frame_feat.clone().requires_grad_(True),
+           "audio_feat": audio_feat.clone().requires_grad_(True)}
+    out = hot_path_forward_train(ins["stage3"], ins["frame_feat"], ins["audio_feat"], q, n_frames, batch_stats)
+    loss = au_loss(out["logits"], labels)
+    if sformer_loss_weight != 0.0:
+        loss = loss + sformer_loss_weight * (out["sformer_out"] * sformer_probe(out["sformer_out"].shape, out["sformer_out"].dtype)).mean()
+    loss.backward()
+    grads = {k: v.grad for k, v in q.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    return loss.detach(), grads, {k: v.grad for k, v in ins.items()}, {k: v.detach() for k, v in out.items()}
+
+
+def sformer_probe(shape, dtype=torch.float32):
+    """Fixed +-1 pattern used as d(loss)/d(sformer_out) direction in hot-path training tests."""
+    n = int(np.prod(shape))
+    idx = np.arange(n, dtype=np.int64)
+    return torch.from_numpy((((idx * 2654435761) >> 7) & 1).astype(np.float64) * 2.0 - 1.0).reshape(shape).to(dtype)
+
+
+def bn_running_update(emb, run_mean, run_var, momentum: float = 0.1):
+    """nn.BatchNorm1d in train(): running = (1-m) running + m batch, with the UNBIASED batch variance."""
+    return ((1 - momentum) * run_mean + momentum * emb.mean(0), (1 - momentum) * run_var + momentum * emb.var(0, unbiased=True))
+
+
+def adam_update(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                decoupled: bool = False):
+    """One step of torch.optim.Adam as train.py:334 configures it (weight decay added to the gradient), or AdamW when
+    ``decoupled``.  Returns the new (param, exp_avg, exp_avg_sq)."""
+    b1, b2 = betas
+    if decoupled:
+        param = param * (1.0 - lr * weight_decay)
+    else:
+        grad = grad + weight_decay * param
+    exp_avg = b1 * exp_avg + (1 - b1) * grad
+    exp_avg_sq = b2 * exp_avg_sq + (1 - b2) * grad * grad
+    denom = exp_avg_sq.sqrt() / math.sqrt(1 - b2 ** step) + eps
+    return param - (lr / (1 - b1 ** step)) * exp_avg / denom, exp_avg, exp_avg_sq
+
+
+# --------------------------------------------------------------------------
 # Deterministic synthetic weights (numpy PCG64: identical in the build container and on the GPU box)
 # --------------------------------------------------------------------------
 def _encoder_spec(pre: str, dim: int, depth: int, inner: int, mlp: int):

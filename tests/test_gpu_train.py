@@ -1,0 +1,311 @@
+"""GPU parity tests of the training step: backward kernels, the whole-path gradients and the fused Adam against the
+CPU oracle (autograd over the restated forward, pinned by tests/golden/grad_T16.npz made from the reference).
+
+Tolerances: fp32 mode — gradients within 1e-4 relative (of each tensor's max-abs) of the oracle / golden values;
+bf16 mode — operands of every GEMM are rounded to bf16 (relative 2^-9 per element), so gradients are compared at
+3e-2 of each tensor's max-abs and 2e-2 on its norm."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import avformer_b200 as A
+from oracle import avformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+AF = A.functional
+
+FP32_RTOL = 1e-4
+BF16_RTOL = 3e-2
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _rel(a, b):
+    b = b.double().cpu()
+    return (a.double().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _model(seed, T, precision, dropout=None):
+    m = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU").set_clip_length(T)
+    m.load_state_dict(O.make_state_dict(seed, T), strict=True)
+    m = m.cuda().set_precision(precision)
+    if dropout is not None:
+        m.set_dropout(dropout)
+    return m
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel level
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb,m,n,k", [(0, 1, 300, 512, 256), (0, 1, 77, 256, 768), (0, 1, 8704, 512, 1024),
+                                          (1, 1, 256, 512, 300), (1, 1, 1536, 512, 4), (1, 1, 768, 256, 50176 // 8),
+                                          (1, 1, 128, 256, 48), (1, 1, 512, 1024, 8704)])
+def test_gemm_operand_modes_tcgen05(ta, tb, m, n, k):
+    """dgrad (NN) and wgrad (TN, split-K) forms against fp64 on bf16-exact inputs."""
+    torch.manual_seed(m + n + k)
+    a = torch.randn((k, m) if ta else (m, k), device="cuda").bfloat16()
+    b = (torch.randn((k, n) if tb else (n, k), device="cuda") / k ** 0.5).bfloat16()
+    A_ = a.double().t() if ta else a.double()
+    B_ = b.double() if tb else b.double().t()
+    ref = A_ @ B_
+    got = AF.gemm(a, b, bool(ta), bool(tb), precision="bf16")
+    assert _rel(got, ref) < 3e-5
+    got32 = AF.gemm(a.float(), b.float(), bool(ta), bool(tb), precision="fp32")
+    assert _rel(got32, ref) < 1e-5
+
+
+def test_gemm_gelu_epilogues():
+    torch.manual_seed(3)
+    m, n, k = 333, 512, 256
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") / k ** 0.5).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    pre = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    g = AF.gemm(a, w, bias=bias, aux=pre, flags=1 | 2 | 16, out_dtype=torch.bfloat16, precision="bf16")
+    ref_pre = a.double() @ w.double().t() + bias.double()
+    assert _rel(pre.float(), ref_pre) < 2 ** -8
+    assert _rel(g.float(), torch.nn.functional.gelu(ref_pre, approximate="tanh")) < 2 ** -7
+    # DGELU: (dy @ W2) * gelu'(pre), W2 stored [K=n2, N=n]
+    n2 = 256
+    dy = torch.randn(m, n2, device="cuda").bfloat16()
+    w2 = (torch.randn(n2, n, device="cuda") / n2 ** 0.5).bfloat16()
+    x = pre.double().requires_grad_(True)
+    torch.nn.functional.gelu(x, approximate="tanh").sum().backward()
+    ref = (dy.double() @ w2.double()) * x.grad
+    got = AF.gemm(dy, w2, False, True, aux=pre, flags=8, out_dtype=torch.float32, precision="bf16")
+    assert _rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 64), (777, 512), (50176, 256), (64, 12544), (5, 6144)])
+def test_colsum(rows, cols):
+    torch.manual_seed(rows)
+    x = torch.randn(rows, cols, device="cuda")
+    assert _rel(AF.colsum(x), x.double().sum(0)) < 1e-5
+    xb = x.bfloat16()
+    assert _rel(AF.colsum(xb), xb.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("dim", [128, 256, 512])
+def test_layernorm_bwd(dim):
+    torch.manual_seed(dim)
+    rows = 1234
+    x = (torch.randn(rows, dim, device="cuda") * 2 + 0.5)
+    gamma = torch.randn(dim, device="cuda")
+    dyn = torch.randn(rows, dim, device="cuda")
+    dres = torch.randn(rows, dim, device="cuda")
+    xr = x.double().cpu().requires_grad_(True)
+    gr = gamma.double().cpu().requires_grad_(True)
+    br = torch.zeros(dim, dtype=torch.float64, requires_grad=True)
+    y = O.layer_norm(xr, gr, br)
+    y.backward(dyn.double().cpu())
+    got, xb, dg, db, dbias = AF.layernorm_bwd_(x, gamma, dyn, dres.clone(), want_bf16=True)
+    assert _rel(got, dres.double().cpu() + xr.grad) < 1e-5
+    assert _rel(xb.float(), dres.double().cpu() + xr.grad) < 2 ** -8
+    assert _rel(dg, gr.grad) < 1e-5 and _rel(db, br.grad) < 1e-5 and _rel(dbias, dres.double().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("n_tok,dh", [(12, 32), (17, 64), (49, 32), (33, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_bwd(n_tok, dh, dtype):
+    torch.manual_seed(n_tok * dh)
+    n_seq, heads = 5, 8
+    inner = heads * dh
+    qkv = torch.randn(n_seq * n_tok, 3 * inner, device="cuda").to(dtype)
+    dout = torch.randn(n_seq * n_tok, inner, device="cuda").to(dtype)
+    q = qkv.double().cpu().requires_grad_(True)
+    qq, kk, vv = (t.reshape(n_seq, n_tok, heads, dh).permute(0, 2, 1, 3) for t in q.chunk(3, dim=-1))
+    att = torch.softmax(qq @ kk.transpose(-1, -2) * dh ** -0.5, dim=-1) @ vv
+    att.permute(0, 2, 1, 3).reshape(n_seq * n_tok, inner).backward(dout.double().cpu())
+    got = AF.attention_bwd(qkv, dout, n_seq, n_tok, heads, dh)
+    assert _rel(got.float(), q.grad) < (1e-5 if dtype == torch.float32 else 2 ** -7)
+
+
+@pytest.mark.parametrize("decoupled", [False, True])
+def test_fused_adam_matches_reference_rule(decoupled):
+    torch.manual_seed(9)
+    n = 100_003
+    p0, m0, v0 = torch.randn(n), torch.zeros(n), torch.zeros(n)
+    p, m, v = p0.cuda(), m0.cuda(), v0.cuda()
+    pr, mr, vr = p0.double(), m0.double(), v0.double()
+    for step in range(1, 4):
+        g = torch.randn(n) * 0.1
+        AF.adam_step_(p, g.cuda(), m, v, step, 5e-4, 0.9, 0.999, 1e-8, 5e-5, decoupled=decoupled)
+        pr, mr, vr = O.adam_update(pr, g.double(), mr, vr, step, 5e-4, (0.9, 0.999), 1e-8, 5e-5, decoupled)
+    assert (p.double().cpu() - pr).abs().max().item() < 1e-6
+    # and torch's own optimiser agrees with the restated rule (pins the oracle)
+    q = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([q], lr=5e-4, weight_decay=5e-5)
+    torch.manual_seed(9)
+    torch.randn(n)
+    for step in range(1, 4):
+        q.grad = torch.randn(n) * 0.1
+        opt.step()
+    assert (q.detach().double() - pr).abs().max().item() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# whole hot path: loss.backward() against the oracle and the golden vectors from the reference
+# ---------------------------------------------------------------------------------------------
+def _hot_path_backward(m, stage3, frame, audio, labels, w_sf):
+    for p_ in m.parameters():
+        p_.grad = None
+    s3 = stage3.cuda().requires_grad_(True)
+    fr = frame.cuda().requires_grad_(True)
+    au = audio.cuda().requires_grad_(True)
+    s_out, out21 = m.hot_path_train(s3, fr, au)
+    loss = m.get_au_loss(out21, labels.cuda())
+    if w_sf:
+        loss = loss + w_sf * (s_out * O.sformer_probe(s_out.shape).cuda()).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.detach(), {"stage3": s3.grad, "frame_feat": fr.grad, "audio_feat": au.grad}, out21.detach()
+
+
+@pytest.mark.parametrize("precision,batch_stats", [("fp32", False), ("fp32", True), ("bf16", False), ("bf16", True)])
+def test_hot_path_gradients_against_oracle(precision, batch_stats):
+    T, B, seed, w_sf = 16, 6, 77, 3.0
+    sd = O.make_state_dict(seed, T, hot_path_only=True)
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2]
+    labels[1, 0] = -1.0                                                  # one ignored row
+    ref_loss, ref_g, ref_in, ref_out = O.hot_path_grads(stage3.double(), frame.double(), audio.double(), labels.double(),
+                                                        O.cast_params(sd, torch.float64), T, batch_stats, w_sf)
+    m = _model(seed, T, precision, dropout=0.0)
+    m.train(batch_stats)
+    run0 = m.video_model.au_head.AU_BN1.running_mean.clone()
+    loss, gin, out21 = _hot_path_backward(m, stage3, frame, audio, labels, w_sf)
+    tol = FP32_RTOL if precision == "fp32" else BF16_RTOL
+    assert abs(loss.item() - ref_loss.item()) < (1e-4 if precision == "fp32" else 2e-2) * max(1.0, abs(ref_loss.item()))
+    for k, g in gin.items():
+        assert _rel(g, ref_in[k]) < tol, f"d{k}: {_rel(g, ref_in[k]):.3e}"
+    named = dict(m.named_parameters())
+    hot = {k: rg for k, rg in ref_g.items() if not O.is_backbone_key(k)}
+    # BatchNorm with batch statistics makes sum_clips d(emb) vanish identically, so gradients that are sums over clips of the
+    # TFormer's cls-row gradient (its last net.3.bias: exactly 0 analytically; cls_token / pos_embedding: mostly cancelled) are
+    # rounding residues.  Their error is therefore measured against the scale of the terms that were summed (1e-3 of the largest
+    # gradient entry of the model) rather than against the residue itself.  In eval mode there is no such floor.
+    floor = 1e-3 * max(rg.abs().max().item() for rg in hot.values()) if batch_stats else 0.0
+    checked = 0
+    for k, rg in hot.items():
+        if rg.abs().max() == 0:
+            continue
+        assert named[k].grad is not None, k
+        err = (named[k].grad.double().cpu() - rg).abs().max().item()
+        r = err / max(rg.abs().max().item(), floor)
+        assert r < tol, f"{k}: rel err {r:.3e} (|ref|max {rg.abs().max().item():.3e}, floor {floor:.3e})"
+        checked += 1
+    assert checked >= 150
+    # parameters the loss never reaches (per-modality AU_linear_last*, models/avformer.py:53,70) get no gradient
+    assert named["video_model.au_head.AU_linear_last1.weight"].grad is None
+    if batch_stats:      # running statistics moved with momentum 0.1 towards the (unbiased) batch statistics
+        cls = ref_out["tformer_cls"]
+        rm, rv = O.bn_running_update(cls, sd["video_model.au_head.AU_BN1.running_mean"].double(), sd["video_model.au_head.AU_BN1.running_var"].double())
+        bn = m.video_model.au_head.AU_BN1
+        assert _rel(bn.running_mean, rm) < (1e-4 if precision == "fp32" else 2e-2) and _rel(bn.running_var, rv) < (1e-4 if precision == "fp32" else 2e-2)
+        assert int(bn.num_batches_tracked) == 1 and not torch.equal(run0, bn.running_mean)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gradients_against_reference_golden(golden_dir, precision):
+    """tests/golden/grad_T16.npz: loss.backward() of the REFERENCE modules (eval mode, fusion head + both AU_formers + TFormer)."""
+    d = dict(np.load(os.path.join(golden_dir, "grad_T16.npz")))
+    T, B, seed = int(d["n_frames"]), int(d["batch"]), int(d["seed"])
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    m = _model(seed, T, precision, dropout=0.0).eval()
+    loss, gin, out21 = _hot_path_backward(m, stage3, frame, audio, torch.from_numpy(d["labels"]), 0.0)
+    tol = FP32_RTOL if precision == "fp32" else BF16_RTOL
+    assert abs(loss.item() - float(d["loss"])) < (1e-4 if precision == "fp32" else 2e-2)
+    assert _rel(out21[:, :12], torch.from_numpy(d["logits"])) < (1e-4 if precision == "fp32" else 2e-2)
+    named = dict(m.named_parameters())
+    n_full = n_norm = 0
+    for k, v in d.items():
+        if k.startswith("g:"):
+            r = _rel(named[k[2:]].grad, torch.from_numpy(v))
+            assert r < tol, f"{k}: {r:.3e}"
+            n_full += 1
+        elif k.startswith("gnorm:"):
+            got = named[k[6:]].grad.double().norm().item()
+            assert abs(got - float(v)) <= (1e-4 if precision == "fp32" else 2e-2) * float(v), f"{k}: {got} vs {float(v)}"
+            n_norm += 1
+    assert n_full > 100 and n_norm > 150
+
+
+def test_frozen_submodels_take_inference_kernels_and_get_no_grads():
+    """Reference default (models/avformer.py:78-85): pretrained sub-models frozen, only the fusion head trains."""
+    T, B, seed = 16, 4, 5
+    m = _model(seed, T, "bf16", dropout=0.0).eval()
+    for p_ in list(m.video_model.parameters()) + list(m.audio_model.parameters()):
+        p_.requires_grad = False
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2]
+    s_out, out21 = m.hot_path_train(stage3.cuda(), frame.cuda(), audio.cuda())
+    assert not s_out.requires_grad and out21.requires_grad
+    m.get_au_loss(out21, labels.cuda()).backward()
+    for k, p_ in m.named_parameters():
+        assert (p_.grad is not None) == (k.startswith("au_head.")), k
+
+
+def test_training_steps_follow_the_oracle_trajectory():
+    """Three optimiser steps on the hot path (fp32 mode, FusedAdam with coupled L2 as train.py:334) against the oracle's
+    own loop: autograd over the restated forward + the restated Adam rule."""
+    T, B, seed, lr, wd = 8, 4, 21, 5e-4, 5e-5
+    sd = O.make_state_dict(seed, T, hot_path_only=True)
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2]
+    m = _model(seed, T, "fp32", dropout=0.0).eval()
+    hot = [p_ for k, p_ in m.named_parameters() if not O.is_backbone_key(k)]
+    opt = A.FusedAdam(hot, lr=lr, weight_decay=wd)
+    p = {k: v.double() for k, v in sd.items()}
+    state = {}
+    losses, ref_losses = [], []
+    for step in range(1, 4):
+        opt.zero_grad()
+        _, out21 = m.hot_path_train(stage3.cuda(), frame.cuda(), audio.cuda())
+        loss = m.get_au_loss(out21, labels.cuda())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        rl, rg, _, _ = O.hot_path_grads(stage3.double(), frame.double(), audio.double(), labels.double(), p, T)
+        ref_losses.append(rl.item())
+        for k, g in rg.items():
+            if O.is_backbone_key(k):
+                continue
+            ea, es = state.get(k, (torch.zeros_like(g), torch.zeros_like(g)))
+            p[k], ea, es = O.adam_update(p[k], g, ea, es, step, lr, (0.9, 0.999), 1e-8, wd)
+            state[k] = (ea, es)
+    assert np.allclose(losses, ref_losses, rtol=2e-4, atol=2e-4), (losses, ref_losses)
+    assert losses[-1] < losses[0]
+    named = dict(m.named_parameters())
+    worst = max(_rel(named[k], p[k]) for k in state)
+    assert worst < 2e-3, worst          # Adam's sign-like first steps amplify 1e-6 gradient noise where |g| ~ eps
+    # parameters without a gradient were not touched (torch.optim.Adam skips grad None)
+    assert torch.equal(named["audio_model.au_head.AU_linear_last3.weight"].cpu(), sd["audio_model.au_head.AU_linear_last3.weight"])
+
+
+def test_full_model_training_step_end_to_end():
+    """model(x) -> get_au_loss -> backward -> FusedAdam.step on the complete drop-in module (conv backbones in torch):
+    gradients reach the backbones through the SFormer / TFormer / AU_former backward kernels, the loss goes down."""
+    T, B, seed = 8, 2, 33
+    m = _model(seed, T, "bf16", dropout=0.0).train()
+    clip, audio, labels = O.synth_inputs(seed, B, T)
+    x = {"clip": clip.cuda(), "audio_features": audio.cuda(), "Index": torch.arange(B).cuda()}
+    opt = A.FusedAdam(m.parameters(), lr=1e-4, weight_decay=5e-5)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        out = m(x)
+        assert out.shape == (B, 21) and float(out[:, 12:].abs().max()) == 0.0
+        loss = m.get_au_loss(out, labels.cuda())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    conv_w = m.video_model.video_model.s_former.conv1.weight
+    assert conv_w.grad is not None and float(conv_w.grad.abs().max()) > 0
+    assert m.audio_model.audio_model.resnet.conv1.weight.grad is not None

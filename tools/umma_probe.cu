@@ -24,13 +24,14 @@ void count_launch() {}
 }  // namespace avf
 using namespace avf;
 
-enum { A_SMEM_SW128 = 0, A_SMEM_SW64 = 1, A_TMEM = 2 };
+enum { A_SMEM_SW128 = 0, A_SMEM_SW64 = 1, A_TMEM = 2, A_MN_SW128 = 3 };
 enum { B_K_SW128 = 0, B_K_SW64 = 1, B_MN_SW64 = 2, B_MN_SW128 = 3 };
 
 struct Params {
   int a_mode, b_mode, n, k;     // m = 128
   int prefill;                  // 1: D pre-filled with `init` through tcgen05.st and MMA accumulates
   uint32_t b_lbo, b_sbo;        // descriptor byte offsets for B
+  uint32_t a_lbo, a_sbo;        // descriptor byte offsets for A (A_MN_SW128)
 };
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
@@ -79,6 +80,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* a, cons
       const int r = i / p.k, c = i % p.k;
       const uint32_t off = uint32_t(r) * 64u + (uint32_t((c >> 3) ^ ((r >> 1) & 3)) << 4) + uint32_t(c & 7) * 2u;
       *reinterpret_cast<__nv_bfloat16*>(sa + off) = a[i];
+    }
+  } else if (p.a_mode == A_MN_SW128) {     // [k rows x 128 m] as two 64-wide panels: row = K index, 128 B of M
+    for (int i = tid; i < 128 * p.k; i += 128) {
+      const int r = i / p.k, c = i % p.k;   // a[r][c]: r = m, c = k
+      *reinterpret_cast<__nv_bfloat16*>(sa + sw128_offset(c, r, p.k)) = a[i];
     }
   } else {                                  // TMEM: lane = row, column j holds elements (2j, 2j+1)
     const int r = tid;
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* a, cons
 
   if (tid == 0) {
     const bool b_mn = p.b_mode >= B_MN_SW64;
-    const uint32_t idesc = make_idesc_bf16(128, p.n, 0, b_mn ? 1 : 0);
+    const uint32_t idesc = make_idesc_bf16(128, p.n, p.a_mode == A_MN_SW128 ? 1 : 0, b_mn ? 1 : 0);
     for (int ks = 0; ks < p.k / 16; ++ks) {
       uint64_t db;
       if (p.b_mode == B_K_SW128) {
@@ -149,7 +155,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const __nv_bfloat16* a, cons
         umma_bf16_ts(TM_D, TM_A + uint32_t(ks * 8), db, idesc, acc);
       } else {
         uint64_t da;
-        if (p.a_mode == A_SMEM_SW128) da = make_desc_sw128_kmajor(smem_u32(sa) + (ks / 4) * 128 * 128) + uint64_t((ks % 4) * 2);
+        if (p.a_mode == A_MN_SW128) da = make_desc(smem_u32(sa) + ks * 2048, p.a_lbo, p.a_sbo, 2);
+        else if (p.a_mode == A_SMEM_SW128) da = make_desc_sw128_kmajor(smem_u32(sa) + (ks / 4) * 128 * 128) + uint64_t((ks % 4) * 2);
         else da = make_desc(smem_u32(sa), 16, 512, 4) + uint64_t(ks * 2);
         umma_bf16(TM_D, da, db, idesc, acc);
       }
@@ -244,6 +251,18 @@ int main() {
       snprintf(nm, sizeof nm, "T3w A tmem, B MN-major sw128 k=128 n=64 lbo=%u sbo=%u", l, s);
       run(nm, {A_TMEM, B_MN_SW128, 64, 128, 0, l, s});
     }
+  const uint32_t lbo3[] = {8192, 16, 1024, 4096};
+  for (uint32_t l : lbo3) {
+    char nm[96];
+    snprintf(nm, sizeof nm, "T7 A MN-major sw128 m=128 k=64 lbo=%u, B K sw128 n=64", l);
+    run(nm, {A_MN_SW128, B_K_SW128, 64, 64, 0, 0, 0, l, 1024});
+    snprintf(nm, sizeof nm, "T8 A K sw128, B MN-major sw128 n=128 k=64 lbo=%u", l);
+    run(nm, {A_SMEM_SW128, B_MN_SW128, 128, 64, 0, l, 1024, 0, 0});
+    snprintf(nm, sizeof nm, "T9 A MN sw128, B MN sw128 n=128 k=64 lbo=%u", l);
+    run(nm, {A_MN_SW128, B_MN_SW128, 128, 64, 0, l, 1024, l, 1024});
+    snprintf(nm, sizeof nm, "T9b A MN sw128, B MN sw128 n=256 k=64 lbo=%u", l);
+    run(nm, {A_MN_SW128, B_MN_SW128, 256, 64, 0, l, 1024, l, 1024});
+  }
   run("T4 prefilled D += A sw128 * B sw128 n=256 k=64", {A_SMEM_SW128, B_K_SW128, 256, 64, 1, 0, 0});
   run("T5 A tmem, B K-major sw128 n=32 k=128 (V^T fallback)", {A_TMEM, B_K_SW128, 32, 128, 0, 0, 0});
   run("T6 A tmem, B K-major sw128 n=128 k=64", {A_TMEM, B_K_SW128, 128, 64, 0, 0, 0});
