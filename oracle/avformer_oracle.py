@@ -306,12 +306,15 @@ def hot_path_grads(stage3, frame_feat, audio_feat, labels, p: P, n_frames: int, 
     ins = {"stage3": stage3.clone().requires_grad_(True), "frame_feat": frame_feat.clone().requires_grad_(True),
            "audio_feat": audio_feat.clone().requires_grad_(True)}
     out = hot_path_forward_train(ins["stage3"], ins["frame_feat"], ins["audio_feat"], q, n_frames, batch_stats)
+    out["tformer_cls"].retain_grad()
     loss = au_loss(out["logits"], labels)
     if sformer_loss_weight != 0.0:
         loss = loss + sformer_loss_weight * (out["sformer_out"] * sformer_probe(out["sformer_out"].shape, out["sformer_out"].dtype)).mean()
     loss.backward()
     grads = {k: v.grad for k, v in q.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
-    return loss.detach(), grads, {k: v.grad for k, v in ins.items()}, {k: v.detach() for k, v in out.items()}
+    gin = {k: v.grad for k, v in ins.items()}
+    gin["tformer_cls"] = out["tformer_cls"].grad          # gradient entering the TFormer's cls rows (scale of the per-clip terms)
+    return loss.detach(), grads, gin, {k: v.detach() for k, v in out.items()}
 
 
 def sformer_probe(shape, dtype=torch.float32):

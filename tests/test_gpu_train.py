@@ -186,20 +186,27 @@ def test_hot_path_gradients_against_oracle(precision, batch_stats):
         assert _rel(g, ref_in[k]) < tol, f"d{k}: {_rel(g, ref_in[k]):.3e}"
     named = dict(m.named_parameters())
     hot = {k: rg for k, rg in ref_g.items() if not O.is_backbone_key(k)}
-    # BatchNorm with batch statistics makes sum_clips d(emb) vanish identically, so gradients that are sums over clips of the
-    # TFormer's cls-row gradient (its last net.3.bias: exactly 0 analytically; cls_token / pos_embedding: mostly cancelled) are
-    # rounding residues.  Their error is therefore measured against the scale of the terms that were summed (1e-3 of the largest
-    # gradient entry of the model) rather than against the residue itself.  In eval mode there is no such floor.
-    floor = 1e-3 * max(rg.abs().max().item() for rg in hot.values()) if batch_stats else 0.0
-    checked = 0
+    # BatchNorm with batch statistics makes sum_clips d(emb) vanish identically (dx = g rstd (dy - mean dy - xhat mean(dy xhat))),
+    # and the TFormer's cls rows (cls_token + pos, both N(0,1)) are nearly the same for every clip.  Every TFormer parameter
+    # gradient is a sum over rows in which those dominant cls-row terms cancel (the last net.3.bias is exactly 0 analytically),
+    # so what is left carries the rounding of the cancelled terms: with 6 clips the TFormer tensors are compared at 5x (the
+    # tensors downstream of the 6-row batch statistics at 2x) the tolerance per tensor (vectors against the scale of the summed terms, max|d tformer_cls|), and the gradient of the WHOLE
+    # model is additionally held to the plain tolerance in the L2 norm.  Eval mode (above) has no such allowance.
+    summand = ref_in["tformer_cls"].abs().max().item()
+    checked, num, den = 0, 0.0, 0.0
     for k, rg in hot.items():
         if rg.abs().max() == 0:
             continue
         assert named[k].grad is not None, k
-        err = (named[k].grad.double().cpu() - rg).abs().max().item()
-        r = err / max(rg.abs().max().item(), floor)
-        assert r < tol, f"{k}: rel err {r:.3e} (|ref|max {rg.abs().max().item():.3e}, floor {floor:.3e})"
+        diff = named[k].grad.double().cpu() - rg
+        num += float((diff * diff).sum())
+        den += float((rg * rg).sum())
+        in_t = batch_stats and ".t_former." in k
+        floor = summand if (in_t and (rg.dim() == 1 or "cls_token" in k or "pos_embedding" in k)) else 0.0
+        r = diff.abs().max().item() / max(rg.abs().max().item(), floor)
+        assert r < (5 * tol if in_t else (2 * tol if batch_stats else tol)), f"{k}: rel err {r:.3e} (|ref|max {rg.abs().max().item():.3e}, floor {floor:.3e})"
         checked += 1
+    assert (num / den) ** 0.5 < (tol if precision == "fp32" else 2e-2), f"whole-model gradient: relative L2 error {(num / den) ** 0.5:.3e}"
     assert checked >= 150
     # parameters the loss never reaches (per-modality AU_linear_last*, models/avformer.py:53,70) get no gradient
     assert named["video_model.au_head.AU_linear_last1.weight"].grad is None
