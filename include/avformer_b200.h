@@ -40,7 +40,8 @@ enum { AVF_EINVAL = -1, AVF_ENODEVICE = -2, AVF_EWORKSPACE = -3, AVF_EUNSUPPORTE
 
 /* epilogue flags of avf_linear_fwd */
 enum { AVF_EPI_BIAS = 1, AVF_EPI_GELU = 2, AVF_EPI_RESIDUAL = 4, AVF_EPI_DGELU = 8 /* x gelu'(aux), training */,
-       AVF_EPI_SAVE_PRE = 16 /* store the pre-GELU value (after bias) to aux, training */ };
+       AVF_EPI_SAVE_PRE = 16 /* store the pre-GELU value (after bias) to aux, training */,
+       AVF_EPI_DROPOUT = 32 /* dropout mask after bias/GELU, before the residual add (internal: needs a seed) */ };
 
 /* One pre-LN encoder layer (models/heads.py:246-250).  Weight matrices are [out, in] row-major
  * exactly as nn.Linear stores them; `w_dtype` says whether they are fp32 or bf16 copies
@@ -194,15 +195,22 @@ int avf_gemm(int mode, int trans_a, int trans_b, const void* a, int32_t lda, con
 
 /* Encoder stack, forward with an activation tape (x is NOT modified; the result goes to out, row stride ld_out)
  * and backward.  dx [n_seq*n_tok, dim] dense fp32 holds the gradient wrt the stack output on entry and the gradient
- * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted). */
+ * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted).
+ * dropout_p > 0 applies nn.Dropout at the reference's three sites per layer (after to_out, after GELU, after net.3;
+ * models/heads.py:216,194,197) with a stateless counter-based mask derived from dropout_seed: the backward call must be given
+ * the same (p, seed) and regenerates the masks instead of storing them.  avf_dropout_mask writes the scaled mask
+ * (0 or 1/(1-p)) of one site (0 = to_out [rows, dim], 1 = GELU [rows, mlp_dim], 2 = net.3 [rows, dim]) for tests. */
 size_t avf_encoder_tape_bytes(const avf_stack_shape* s, int mode);
 size_t avf_encoder_bwd_workspace_bytes(const avf_stack_shape* s, int mode);
 int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
                                 const float* x, int32_t ld_x, float* out, int32_t ld_out,
-                                void* tape, size_t tape_bytes, void* stream);
+                                void* tape, size_t tape_bytes, float dropout_p, uint64_t dropout_seed, void* stream);
 int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
                           const void* tape, size_t tape_bytes, float* dx, int32_t ld_dx,
-                          const avf_layer_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+                          const avf_layer_grads* grads, void* workspace, size_t workspace_bytes,
+                          float dropout_p, uint64_t dropout_seed, void* stream);
+int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, int32_t layer, int32_t site, int32_t rows, int32_t cols,
+                     float* out, void* stream);
 
 /* Building blocks of the backward pass (exposed for tests). */
 /* out[c] = sum_r x[r, c]; x is fp32 or bf16 per in_mode with row stride ld (elements). */

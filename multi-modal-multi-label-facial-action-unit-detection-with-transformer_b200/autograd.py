@@ -26,7 +26,8 @@ class EncoderStackFn(torch.autograd.Function):
     def forward(ctx, x, tr, n_seq, n_tok, *params):
         packed = tr.packed()
         shape = tr.shape(n_seq, n_tok)
-        y, tape = AF.encoder_stack_fwd_train(_f32_dense(x.detach()), packed, shape)
+        ctx.drop = tr.dropout_state()
+        y, tape = AF.encoder_stack_fwd_train(_f32_dense(x.detach()), packed, shape, *ctx.drop)
         ctx.packed, ctx.shape_, ctx.tape = packed, shape, tape
         return y
 
@@ -34,7 +35,7 @@ class EncoderStackFn(torch.autograd.Function):
     def backward(ctx, dy):
         needs = ctx.needs_input_grad
         dx = _f32_dense(dy).clone()
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]))
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop)
         ctx.tape = None
         return (dx if needs[0] else None, None, None, None, *grads)
 
@@ -48,7 +49,8 @@ class SFormerFn(torch.autograd.Function):
         packed = tr.packed()
         shape = tr.shape(F_, H * W)
         x = AF.sformer_tokens_pack(fmap.detach(), pos.detach().reshape(-1, C)[: H * W])
-        y, tape = AF.encoder_stack_fwd_train(x, packed, shape)
+        ctx.drop = tr.dropout_state()
+        y, tape = AF.encoder_stack_fwd_train(x, packed, shape, *ctx.drop)
         ctx.packed, ctx.shape_, ctx.tape, ctx.fshape, ctx.fdtype, ctx.pos_shape = packed, shape, tape, (F_, C, H, W), fmap.dtype, pos.shape
         return AF.sformer_tokens_unpack(y, (F_, C, H, W), fmap.dtype)
 
@@ -57,7 +59,7 @@ class SFormerFn(torch.autograd.Function):
         needs = ctx.needs_input_grad
         F_, C, H, W = ctx.fshape
         dx = AF.sformer_tokens_pack(dout, None)
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]))
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]), *ctx.drop)
         ctx.tape = None
         dpos = None
         if needs[1]:

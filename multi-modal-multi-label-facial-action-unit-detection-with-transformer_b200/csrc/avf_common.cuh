@@ -65,6 +65,21 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * fmaf(3.0f * 0.044715f, x2, 1.0f);
 }
 
+// Dropout (nn.Dropout of models/heads.py:194,197,216) as a stateless counter-based mask: element `idx` of site `seed` is kept
+// iff murmur3-finaliser(idx * golden ^ seed) >= thresh, kept values are scaled by 1/(1-p).  The same (seed, idx) regenerates the
+// mask in the backward pass, so no mask is ever stored.
+struct DropSpec {
+  uint32_t seed = 0, thresh = 0;     // thresh = round(p * 2^32); 0 disables
+  float scale = 1.f;                 // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ float drop_factor(const DropSpec& d, uint32_t idx) {
+  return mix32(idx * 0x9E3779B1u ^ d.seed) >= d.thresh ? d.scale : 0.f;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -45,7 +45,7 @@ struct GemmCfg {
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
                                                const float* __restrict__ bias, const float* res, int ld_res, int flags,
-                                               __nv_bfloat16* aux, int ld_aux) {
+                                               __nv_bfloat16* aux, int ld_aux, const DropSpec& drop, int n_total) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -85,6 +85,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = gelu_tanh<true>(f[j]);
   }
+  if (flags & AVF_EPI_DROPOUT) {
+    const uint32_t i0 = uint32_t(row) * uint32_t(n_total) + uint32_t(col0);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= drop_factor(drop, i0 + j);
+  }
   if (flags & AVF_EPI_RESIDUAL) {
     const float* rp = res + size_t(row) * ld_res + col0;
 #pragma unroll
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(384, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                  OutT* C, int ldc, const float* __restrict__ bias,
                  const float* res, int ld_res, int M, int N, int K, int flags,
-                 __nv_bfloat16* aux, int ld_aux, int splits, size_t split_stride) {
+                 __nv_bfloat16* aux, int ld_aux, int splits, size_t split_stride, DropSpec drop) {
   using Cfg = GemmCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -240,7 +245,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux);
+        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N);
       }
     }
   }
@@ -302,7 +307,7 @@ static int sm_count() {
 template <int BN, int STAGES, typename OutT, bool A_MN, bool B_MN>
 static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, int ldc, const float* bias,
                        const float* res, int ld_res, int m, int n, int k, int flags, const void* aux, int ld_aux,
-                       int splits, size_t split_stride, cudaStream_t stream) {
+                       int splits, size_t split_stride, cudaStream_t stream, DropSpec drop = DropSpec{}) {
   using Cfg = GemmCfg<BN, STAGES>;
   CUtensorMap ta, tw;
   // K-major operand: [rows = M|N, cols = K], box 64 x {128|BN}.  MN-major operand: [rows = K, cols = M|N], box 64 x 64.
@@ -318,7 +323,7 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
   }
   const int n_tiles = (n / BN) * ceil_div(m, BM) * splits;
   kern<<<min(n_tiles, sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
-                                                                   static_cast<__nv_bfloat16*>(const_cast<void*>(aux)), ld_aux, splits, split_stride);
+                                                                   static_cast<__nv_bfloat16*>(const_cast<void*>(aux)), ld_aux, splits, split_stride, drop);
   AVF_LAUNCH_CHECK("gemm_umma_kernel");
   return 0;
 }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // partial tiles and a second kernel reduces them in a fixed order (bit-reproducible).
 int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, int ldw, const float* bias, const float* res,
               int ld_res, const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags,
-              void* ws, size_t ws_bytes, cudaStream_t stream) {
+              void* ws, size_t ws_bytes, cudaStream_t stream, DropSpec drop) {
   AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
   AVF_REQUIRE(n % 64 == 0, AVF_EUNSUPPORTED, "linear(bf16): N=%d must be a multiple of 64", n);
   AVF_REQUIRE(trans_a || trans_b || k % 8 == 0, AVF_EUNSUPPORTED, "linear(bf16): K=%d must be a multiple of 8", k);
@@ -390,8 +395,8 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
 #define AVF_GEMM(BN_, ST_, BMN_)                                                                                                   \
   if (bn == BN_ && bool(trans_b) == BMN_) {                                                                                        \
     if (c_mode == AVF_BF16)                                                                                                        \
-      return launch_gemm<BN_, ST_, __nv_bfloat16, false, BMN_>(a, lda, w, ldw, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream); \
-    return launch_gemm<BN_, ST_, float, false, BMN_>(a, lda, w, ldw, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream);          \
+      return launch_gemm<BN_, ST_, __nv_bfloat16, false, BMN_>(a, lda, w, ldw, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream, drop); \
+    return launch_gemm<BN_, ST_, float, false, BMN_>(a, lda, w, ldw, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags, aux, ld_aux, 1, 0, stream, drop);          \
   }
   AVF_GEMM(256, 4, false)
   AVF_GEMM(128, 6, false)
@@ -414,7 +419,7 @@ size_t gemm_umma_workspace_bytes(int m, int n, int k) {       // for the TN (wgr
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c,
                 int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t stream) {
   AVF_REQUIRE(k % BK == 0, AVF_EUNSUPPORTED, "linear(bf16): K=%d must be a multiple of %d", k, BK);
-  return gemm_umma(0, 0, a, lda, w, k, bias, res, ld_res, nullptr, 0, c, ldc, c_mode, m, n, k, flags, nullptr, 0, stream);
+  return gemm_umma(0, 0, a, lda, w, k, bias, res, ld_res, nullptr, 0, c, ldc, c_mode, m, n, k, flags, nullptr, 0, stream, DropSpec{});
 }
 
 }  // namespace avf

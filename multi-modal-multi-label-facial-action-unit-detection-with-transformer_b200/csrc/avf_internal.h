@@ -4,6 +4,7 @@
 #include <stddef.h>
 
 #include "../../include/avformer_b200.h"
+#include "avf_common.cuh"
 
 namespace avf {
 
@@ -27,14 +28,21 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
 int attention_small(int io_mode, const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
 int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, int ldw, const float* bias, const float* res, int ld_res,
-             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st);
+             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st, DropSpec drop = DropSpec{});
 
 // avf_train.cu
 size_t colsum_workspace_bytes(int rows, int cols);
 int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out, float beta, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t layernorm_bwd_workspace_bytes(int rows, int dim);
-int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, float* dgamma,
-                  float* dbeta, float* dbias, float beta_acc, int rows, int dim, void* ws, size_t ws_bytes, cudaStream_t st);
+// drop_in masks the incoming dres for the dbias sums (dropout on the output of the sub-layer being differentiated);
+// drop_out masks the copy written to dxb (dropout on the output of the sub-layer BELOW, whose GEMMs consume dxb).
+// dxb is bf16 (dxb_mode AVF_BF16) or fp32.
+int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, int dxb_mode, float* dgamma,
+                  float* dbeta, float* dbias, float beta_acc, int rows, int dim, void* ws, size_t ws_bytes, cudaStream_t st,
+                  DropSpec drop_in = DropSpec{}, DropSpec drop_out = DropSpec{});
+// y = x * mask(drop) as bf16 / fp32 (dense [rows, dim]); without dropout a plain cast / copy
+int masked_copy(const float* x, void* y, int y_mode, int rows, int dim, DropSpec drop, cudaStream_t st);
+int dropout_mask(float* out, int rows, int cols, DropSpec drop, cudaStream_t st);
 int attention_bwd(int io_mode, const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 int au_logits_bwd(const float* dl, int ld_dl, const float* x, int ld_x, const float* w_last, float* dx, int ld_dx, float* dw, int n_clips,
                   int dim, cudaStream_t st);
@@ -57,7 +65,7 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
 // avf_gemm_umma.cu
 int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, int ldw, const float* bias, const float* res, int ld_res,
               const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, void* ws, size_t ws_bytes,
-              cudaStream_t stream);
+              cudaStream_t stream, DropSpec drop = DropSpec{});
 size_t gemm_umma_workspace_bytes(int m, int n, int k);
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
                 int c_mode, int m, int n, int k, int flags, cudaStream_t st);

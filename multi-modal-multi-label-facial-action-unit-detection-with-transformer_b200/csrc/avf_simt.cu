@@ -64,7 +64,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __restrict__ A, long a_rs, long a_cs, const float* __restrict__ W,
                                                                long w_rs, long w_cs, OutT* __restrict__ C, int ldc,
                                                                const float* __restrict__ bias, const float* __restrict__ res, int ld_res,
-                                                               float* aux, int ld_aux, int M, int N, int K, int flags) {
+                                                               float* aux, int ld_aux, int M, int N, int K, int flags, DropSpec drop) {
   __shared__ float As[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __re
       if (flags & AVF_EPI_BIAS) v += bias[c];
       if (flags & AVF_EPI_SAVE_PRE) aux[size_t(r) * ld_aux + c] = v;
       if (flags & AVF_EPI_GELU) v = gelu_tanh<false>(v);
+      if (flags & AVF_EPI_DROPOUT) v *= drop_factor(drop, uint32_t(r) * uint32_t(N) + uint32_t(c));
       if (flags & AVF_EPI_RESIDUAL) v += res[size_t(r) * ld_res + c];
       C[size_t(r) * ldc + c] = from_f32<OutT>(v);
     }
@@ -230,17 +231,17 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
 }
 
 int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, int ldw, const float* bias, const float* res, int ld_res,
-             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st) {
+             float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st, DropSpec drop) {
   AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
   AVF_REQUIRE(!(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) || aux != nullptr, AVF_EINVAL, "linear(fp32): DGELU / SAVE_PRE epilogues need the pre-activation buffer");
-  if (!trans_a && !trans_b && ldw == k && !(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) && k % 16 == 0 && lda % 4 == 0)
+  if (!trans_a && !trans_b && ldw == k && !(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE | AVF_EPI_DROPOUT)) && k % 16 == 0 && lda % 4 == 0)
     return linear_f32(a, lda, w, bias, res, ld_res, c, ldc, c_mode, m, n, k, flags, st);
   dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
   const long a_rs = trans_a ? 1 : lda, a_cs = trans_a ? lda : 1, w_rs = trans_b ? 1 : ldw, w_cs = trans_b ? ldw : 1;
   if (c_mode == AVF_BF16)
-    gemm_f32_generic_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags);
+    gemm_f32_generic_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
   else
-    gemm_f32_generic_kernel<float><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<float*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags);
+    gemm_f32_generic_kernel<float><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<float*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
   AVF_LAUNCH_CHECK("gemm_f32_generic_kernel");
   return 0;
 }

@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 template <int VEC>   // DIM = 128 * VEC
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
                                                             const float* __restrict__ dyn, float* dres, int ld_d,
-                                                            __nv_bfloat16* __restrict__ dxb, float* __restrict__ part, int rows,
-                                                            int rows_per_block) {
+                                                            void* __restrict__ dxb, int dxb_bf16, float* __restrict__ part, int rows,
+                                                            int rows_per_block, DropSpec drop_in, DropSpec drop_out) {
   constexpr int DIM = 128 * VEC;
   __shared__ float red[8][DIM];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +111,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float4 r = dp[lane + 32 * i];
-      ad[i].x += r.x; ad[i].y += r.y; ad[i].z += r.z; ad[i].w += r.w;
+      if (drop_in.thresh != 0) {      // bias gradient of a sub-layer whose output went through dropout: sum the masked gradient
+        const uint32_t i0 = uint32_t(row) * DIM + (lane + 32 * i) * 4;
+        ad[i].x += r.x * drop_factor(drop_in, i0); ad[i].y += r.y * drop_factor(drop_in, i0 + 1);
+        ad[i].z += r.z * drop_factor(drop_in, i0 + 2); ad[i].w += r.w * drop_factor(drop_in, i0 + 3);
+      } else {
+        ad[i].x += r.x; ad[i].y += r.y; ad[i].z += r.z; ad[i].w += r.w;
+      }
       float4 o;
       o.x = r.x + rstd * (g[i].x - m1 - v[i].x * m2);
       o.y = r.y + rstd * (g[i].y - m1 - v[i].y * m2);
@@ -119,10 +125,20 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       o.w = r.w + rstd * (g[i].w - m1 - v[i].w * m2);
       dp[lane + 32 * i] = o;
       if (dxb != nullptr) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o.x, o.y);
-        pk.y = pack_bf16x2(o.z, o.w);
-        *reinterpret_cast<uint2*>(dxb + size_t(row) * DIM + (lane + 32 * i) * 4) = pk;
+        if (drop_out.thresh != 0) {
+          const uint32_t i0 = uint32_t(row) * DIM + (lane + 32 * i) * 4;
+          o.x *= drop_factor(drop_out, i0); o.y *= drop_factor(drop_out, i0 + 1);
+          o.z *= drop_factor(drop_out, i0 + 2); o.w *= drop_factor(drop_out, i0 + 3);
+        }
+        const size_t off = size_t(row) * DIM + (lane + 32 * i) * 4;
+        if (dxb_bf16) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o.x, o.y);
+          pk.y = pack_bf16x2(o.z, o.w);
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(dxb) + off) = pk;
+        } else {
+          *reinterpret_cast<float4*>(static_cast<float*>(dxb) + off) = o;
+        }
       }
     }
   }
@@ -143,6 +159,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       pb[q * DIM + c] = a;
     }
   }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) masked_copy_kernel(const float* __restrict__ x, OutT* __restrict__ y, size_t n, DropSpec drop) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = from_f32<OutT>(x[i] * drop_factor(drop, uint32_t(i)));
+}
+__global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, size_t n, DropSpec drop) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = drop_factor(drop, uint32_t(i));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -419,8 +445,9 @@ int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out
 static int ln_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 8), 296)); }
 size_t layernorm_bwd_workspace_bytes(int rows, int dim) { return size_t(ln_bwd_blocks(rows)) * 3 * dim * sizeof(float); }
 
-int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, float* dgamma,
-                  float* dbeta, float* dbias, float beta_acc, int rows, int dim, void* ws, size_t ws_bytes, cudaStream_t st) {
+int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, int dxb_mode, float* dgamma,
+                  float* dbeta, float* dbias, float beta_acc, int rows, int dim, void* ws, size_t ws_bytes, cudaStream_t st,
+                  DropSpec drop_in, DropSpec drop_out) {
   AVF_REQUIRE(rows > 0 && x && gamma && dyn && dres, AVF_EINVAL, "layernorm_bwd: null pointer / rows=%d", rows);
   AVF_REQUIRE(dim % 128 == 0 && dim <= 512 && ld_x % 4 == 0 && ld_d % 4 == 0, AVF_EUNSUPPORTED,
               "layernorm_bwd: dim=%d must be a multiple of 128, <= 512", dim);
@@ -429,18 +456,35 @@ int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn
   const int rpb = ceil_div(rows, blocks);
   const int grid = ceil_div(rows, rpb);
   float* part = static_cast<float*>(ws);
-  __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(dxb);
+  const int xb16 = dxb_mode == AVF_BF16 ? 1 : 0;
   switch (dim / 128) {
-    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, xb, part, rows, rpb); break;
-    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, xb, part, rows, rpb); break;
-    case 3: layernorm_bwd_kernel<3><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, xb, part, rows, rpb); break;
-    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, xb, part, rows, rpb); break;
+    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    case 3: layernorm_bwd_kernel<3><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
   }
   AVF_LAUNCH_CHECK("layernorm_bwd_kernel");
   if (dgamma || dbeta || dbias) {
     colsum_final_kernel<<<ceil_div(3 * dim, 256), 256, 0, st>>>(part, grid, dim, 3, dgamma, dbeta, dbias, beta_acc);
     AVF_LAUNCH_CHECK("colsum_final_kernel");
   }
+  return 0;
+}
+
+int masked_copy(const float* x, void* y, int y_mode, int rows, int dim, DropSpec drop, cudaStream_t st) {
+  const size_t n = size_t(rows) * dim;
+  AVF_REQUIRE(n > 0 && n < (size_t(1) << 32), AVF_EINVAL, "masked_copy: %zu elements", n);
+  if (y_mode == AVF_BF16) masked_copy_kernel<__nv_bfloat16><<<unsigned((n + 255) / 256), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(y), n, drop);
+  else masked_copy_kernel<float><<<unsigned((n + 255) / 256), 256, 0, st>>>(x, static_cast<float*>(y), n, drop);
+  AVF_LAUNCH_CHECK("masked_copy_kernel");
+  return 0;
+}
+
+int dropout_mask(float* out, int rows, int cols, DropSpec drop, cudaStream_t st) {
+  const size_t n = size_t(rows) * cols;
+  AVF_REQUIRE(out && n > 0 && n < (size_t(1) << 32), AVF_EINVAL, "dropout_mask: %zu elements", n);
+  dropout_mask_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(out, n, drop);
+  AVF_LAUNCH_CHECK("dropout_mask_kernel");
   return 0;
 }
 

@@ -123,6 +123,7 @@ class Transformer(nn.Module):
                            Residual(PreNorm(dim, FeedForward(dim, mlp_dim, dropout=dropout)))])
             for _ in range(depth)])
         self.precision: Optional[str] = None       # None -> default_precision()
+        self.fixed_dropout_seed: Optional[int] = None
         self._packed: Optional[AF.PackedStack] = None
 
     # -- weights -------------------------------------------------------------------------------
@@ -149,20 +150,34 @@ class Transformer(nn.Module):
         names = [n for n, _ in AF.LayerWeights._fields_]
         return [lw[n] for lw in self._layer_tensors() for n in names]
 
-    def _check_dropout(self):
-        if self.training and self.dropout > 0.0:
-            raise NotImplementedError("avformer_b200: dropout>0 in train() mode is not implemented; set_dropout(0.0) or eval()")
+    def dropout_state(self):
+        """(p, seed) of the next training forward: p = 0 in eval(); the seed is drawn from torch's default generator so that
+        torch.manual_seed makes runs reproducible.  ``fixed_dropout_seed`` (tests) pins it."""
+        if not self.training or self.dropout <= 0.0:
+            return 0.0, 0
+        seed = self.fixed_dropout_seed
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return float(self.dropout), seed
 
     # -- forward -------------------------------------------------------------------------------
     def forward_(self, x2d: torch.Tensor, n_seq: int, n_tok: int, out: Optional[torch.Tensor] = None, ld_out: int = 0) -> torch.Tensor:
-        """Inference kernels, in place on an fp32 residual stream [n_seq*n_tok, dim]."""
-        self._check_dropout()
+        """Inference kernels, in place on an fp32 residual stream [n_seq*n_tok, dim].  In train() mode with dropout > 0 (a
+        frozen sub-model inside a training loop, models/avformer.py:78-85 + train.py:327) the tape-keeping kernels run instead,
+        because they are the ones that apply dropout."""
+        p, seed = self.dropout_state()
+        if p > 0.0:
+            y, _ = AF.encoder_stack_fwd_train(x2d, self.packed(), self.shape(n_seq, n_tok), p, seed)
+            if out is None:
+                x2d.copy_(y)
+                return x2d
+            torch.as_strided(out, (y.shape[0], y.shape[1]), (ld_out, 1)).copy_(y)
+            return out
         return AF.encoder_stack_fwd_(x2d, self.packed(), self.shape(n_seq, n_tok), out, ld_out)
 
     def forward_train(self, x2d: torch.Tensor, n_seq: int, n_tok: int) -> torch.Tensor:
         """Autograd-visible forward on an fp32 token matrix [n_seq*n_tok, dim] (activation tape kept for backward)."""
         from .autograd import EncoderStackFn
-        self._check_dropout()
         return EncoderStackFn.apply(x2d, self, n_seq, n_tok, *self.param_list())
 
     def forward(self, x: torch.Tensor, mask=None) -> torch.Tensor:

@@ -94,8 +94,7 @@ class ResFormer(nn.Module):
         n_tok = fmap.shape[2] * fmap.shape[3]
         if n_tok > self.pos_embedding.shape[1]:
             raise ValueError(f"stage-3 map has {n_tok} positions but pos_embedding holds {self.pos_embedding.shape[1]}")
-        st._check_dropout()
-        if needs_grad(st, fmap, self.pos_embedding):
+        if needs_grad(st, fmap, self.pos_embedding) or st.dropout_state()[0] > 0.0:
             from .autograd import SFormerFn
             return SFormerFn.apply(fmap, self.pos_embedding, st, *st.param_list())
         return AF.sformer_fwd(fmap, self.pos_embedding[0, :n_tok], st.packed(), st.heads, st.dim_head, st.mlp_dim)

@@ -60,10 +60,11 @@ def layer_norm(x, g, b, eps: float = 1e-5):
     return (x - mu) / torch.sqrt(var + eps) * g + b
 
 
-def attention(x, p: P, pre: str, heads: int):
+def attention(x, p: P, pre: str, heads: int, drop=None):
     """models/heads.py:203-239.  x [B,N,D]; to_qkv has no bias, its output columns are
     [q | k | v], each split head-major '(h d)' (:221-222); scale dh**-0.5 (:210,:224);
-    softmax over keys (:234); heads merged 'b h n d -> b n (h d)' (:237); to_out.0 with bias."""
+    softmax over keys (:234); heads merged 'b h n d -> b n (h d)' (:237); to_out.0 with bias, then
+    Dropout (:216; ``drop`` is a callable applying an explicit scaled keep-mask, identity when None)."""
     B, N, _ = x.shape
     wqkv = p[pre + "fn.fn.to_qkv.weight"]
     inner = wqkv.shape[0] // 3
@@ -73,30 +74,40 @@ def attention(x, p: P, pre: str, heads: int):
     dots = torch.matmul(q, k.transpose(-1, -2)) * (dh ** -0.5)
     attn = torch.softmax(dots, dim=-1)
     out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(B, N, inner)
-    return out @ p[pre + "fn.fn.to_out.0.weight"].t() + p[pre + "fn.fn.to_out.0.bias"]
+    y = out @ p[pre + "fn.fn.to_out.0.weight"].t() + p[pre + "fn.fn.to_out.0.bias"]
+    return y if drop is None else drop(0, y)
 
 
-def feed_forward(x, p: P, pre: str):
-    """models/heads.py:188-200 — Linear(D,M)+b, GELU, Linear(M,D)+b (dropouts are identity in eval)."""
+def feed_forward(x, p: P, pre: str, drop=None):
+    """models/heads.py:188-200 — Linear(D,M)+b, GELU, Dropout, Linear(M,D)+b, Dropout (identity in eval / when
+    ``drop`` is None; otherwise drop(site, tensor) with site 1 after the GELU and 2 after net.3)."""
     h = gelu_tanh(x @ p[pre + "fn.fn.net.0.weight"].t() + p[pre + "fn.fn.net.0.bias"])
-    return h @ p[pre + "fn.fn.net.3.weight"].t() + p[pre + "fn.fn.net.3.bias"]
+    if drop is not None:
+        h = drop(1, h)
+    y = h @ p[pre + "fn.fn.net.3.weight"].t() + p[pre + "fn.fn.net.3.bias"]
+    return y if drop is None else drop(2, y)
 
 
-def encoder_layer(x, p: P, pre: str, heads: int):
+def encoder_layer(x, p: P, pre: str, heads: int, drop=None):
     """One (Residual(PreNorm(Attention)), Residual(PreNorm(FeedForward))) pair,
     models/heads.py:169-185,246-250.  ``pre`` ends in 'layers.L.'."""
     a = pre + "0."
-    x = x + attention(layer_norm(x, p[a + "fn.norm.weight"], p[a + "fn.norm.bias"]), p, a, heads)
+    x = x + attention(layer_norm(x, p[a + "fn.norm.weight"], p[a + "fn.norm.bias"]), p, a, heads, drop)
     f = pre + "1."
-    x = x + feed_forward(layer_norm(x, p[f + "fn.norm.weight"], p[f + "fn.norm.bias"]), p, f)
+    x = x + feed_forward(layer_norm(x, p[f + "fn.norm.weight"], p[f + "fn.norm.bias"]), p, f, drop)
     return x
 
 
-def transformer(x, p: P, pre: str, depth: int, heads: int):
+def transformer(x, p: P, pre: str, depth: int, heads: int, masks=None):
     """models/heads.py:242-256 — depth x encoder_layer, no final norm.  ``pre`` ends in
-    'spatial_transformer.' or 'corr_transformer.'."""
+    'spatial_transformer.' or 'corr_transformer.'.  ``masks[(layer, site)]`` are explicit scaled keep-masks
+    (0 or 1/(1-p), shaped like the tensor flattened to [B*N, width]) for train()-mode dropout; the reference draws
+    them from torch's Philox stream, which cannot be reproduced bit-for-bit, so tests inject the masks instead."""
     for l in range(depth):
-        x = encoder_layer(x, p, f"{pre}layers.{l}.", heads)
+        drop = None
+        if masks is not None:
+            drop = (lambda site, t, l=l: t * masks[(l, site)].reshape(t.shape).to(t.dtype))
+        x = encoder_layer(x, p, f"{pre}layers.{l}.", heads, drop)
     return x
 
 

@@ -316,3 +316,72 @@ def test_full_model_training_step_end_to_end():
     conv_w = m.video_model.video_model.s_former.conv1.weight
     assert conv_w.grad is not None and float(conv_w.grad.abs().max()) > 0
     assert m.audio_model.audio_model.resnet.conv1.weight.grad is not None
+
+
+# ---------------------------------------------------------------------------------------------
+# dropout (train() mode of the audio AU_former and the fusion head: p = 0.2, models/avformer.py:48,87)
+# ---------------------------------------------------------------------------------------------
+def test_dropout_mask_statistics_and_determinism():
+    p, seed = 0.2, 123456789
+    m = AF.dropout_mask(p, seed, 1, 2, 4096, 256, "cuda")
+    vals = torch.unique(m)
+    assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.25) < 1e-6
+    keep = (m > 0).float().mean().item()
+    assert abs(keep - 0.8) < 3e-3                                   # 1M samples: 4 sigma = 1.6e-3
+    assert abs((m > 0).float().mean(0).std().item() - (0.8 * 0.2 / 4096) ** 0.5) < 2e-3     # no column structure
+    assert torch.equal(m, AF.dropout_mask(p, seed, 1, 2, 4096, 256, "cuda"))
+    for other in (AF.dropout_mask(p, seed + 1, 1, 2, 4096, 256, "cuda"), AF.dropout_mask(p, seed, 0, 2, 4096, 256, "cuda"),
+                  AF.dropout_mask(p, seed, 1, 0, 4096, 256, "cuda")):
+        agree = ((other > 0) == (m > 0)).float().mean().item()
+        assert abs(agree - (0.8 * 0.8 + 0.2 * 0.2)) < 5e-3          # independent masks agree 68 % of the time
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("dim,depth,mlp,n_tok", [(256, 3, 256, 12), (128, 2, 256, 12)])
+def test_encoder_stack_with_dropout_against_oracle_with_the_same_masks(precision, dim, depth, mlp, n_tok):
+    """Forward and backward of a whole stack in train() mode: the kernels' counter-based masks are read back through
+    avf_dropout_mask and injected into the oracle, so dropout is checked exactly (values, scaling, placement, gradients)."""
+    torch.manual_seed(dim + depth)
+    n_seq, heads, dh, p_drop, seed = 9, 8, 32, 0.2, 987654321
+    tr = A.Transformer(dim, depth, heads, dh, mlp, dropout=p_drop).cuda().train()
+    tr.precision = precision
+    tr.fixed_dropout_seed = seed
+    with torch.no_grad():
+        for q in tr.parameters():
+            if q.dim() == 1:
+                q.add_(torch.randn_like(q) * 0.1)
+    x = torch.randn(n_seq, n_tok, dim, device="cuda", requires_grad=True)
+    dy = torch.randn(n_seq, n_tok, dim, device="cuda")
+    y = tr(x)
+    y.backward(dy)
+    R = n_seq * n_tok
+    masks = {(l, s): AF.dropout_mask(p_drop, seed, l, s, R, mlp if s == 1 else dim, "cuda").double().cpu() for l in range(depth) for s in range(3)}
+    pr = {"t." + k: v.detach().double().cpu().requires_grad_(True) for k, v in tr.named_parameters()}
+    xr = x.detach().double().cpu().requires_grad_(True)
+    yr = O.transformer(xr, pr, "t.", depth, heads, masks)
+    yr.backward(dy.double().cpu())
+    tol_y, tol_g = (1e-4, 1e-4) if precision == "fp32" else (2e-2, 3e-2)
+    assert _rel(y, yr.detach()) < tol_y
+    assert _rel(x.grad, xr.grad) < tol_g
+    for k, v in tr.named_parameters():
+        assert _rel(v.grad, pr["t." + k].grad) < tol_g, k
+    # eval() switches dropout off (same kernels, p = 0)
+    tr.eval()
+    y_eval = tr(x.detach())
+    assert _rel(y_eval, O.transformer(xr.detach(), {k: v.detach() for k, v in pr.items()}, "t.", depth, heads)) < tol_y
+
+
+def test_train_mode_model_uses_dropout_and_stays_finite():
+    T, B, seed = 16, 8, 12
+    m = _model(seed, T, "bf16").train()          # reference rates: 0.2 in the audio AU_former and the fusion head
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2]
+    torch.manual_seed(0)
+    _, a = m.hot_path_train(stage3.cuda(), frame.cuda(), audio.cuda())
+    torch.manual_seed(0)
+    _, b = m.hot_path_train(stage3.cuda(), frame.cuda(), audio.cuda())
+    torch.manual_seed(1)
+    _, c = m.hot_path_train(stage3.cuda(), frame.cuda(), audio.cuda())
+    assert torch.equal(a, b) and not torch.equal(a, c)            # reproducible under torch.manual_seed, random otherwise
+    m.get_au_loss(c, labels.cuda()).backward()
+    assert all(torch.isfinite(q.grad).all() for q in m.au_head.parameters())
