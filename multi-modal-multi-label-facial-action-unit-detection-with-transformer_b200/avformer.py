@@ -170,6 +170,57 @@ class TwoStreamAuralVisualFormer(nn.Module):
         res = self.au_head.logits21_(fused, n_clips, want_decisions)
         return (s_out,) + (res if want_decisions else (res,))
 
+    def hot_path_from_host(self, stage3_host, frame_host, audio_host, out_host=None, dec_host=None, chunks: int = 4):
+        """hot_path() for inputs that still sit in (pinned) HOST memory: the public end-to-end entry bench.py's ``e2e`` times.
+
+        The stage-3 maps are 95 % of the bytes.  They are copied in ``chunks`` pieces on a dedicated copy stream while the
+        compute stream first runs the TFormer / AU_former / fusion-head chain (whose small inputs are copied first) and then
+        the fused SFormer kernel chunk by chunk, each launch waiting only for its own piece — so the kernels hide behind
+        the PCIe transfer instead of queueing after it.  Logits (and int32 decisions) are copied back into ``out_host`` /
+        ``dec_host`` (pinned) when given.  Returns (sformer_out [device], out21 [device], decisions [device])."""
+        dev = self.au_head.pos_embedding.device
+        if not dev.type == "cuda":
+            raise RuntimeError("avformer_b200: the model is not on a CUDA device; the B200 path has no CPU fallback")
+        key = (tuple(stage3_host.shape), stage3_host.dtype, tuple(frame_host.shape), frame_host.dtype, tuple(audio_host.shape), chunks)
+        st = getattr(self, "_host_staging", None)
+        if st is None or st["key"] != key:
+            n = stage3_host.shape[0]
+            bounds = [(n * i // chunks, n * (i + 1) // chunks) for i in range(chunks)]
+            st = self._host_staging = {
+                "key": key, "bounds": [b for b in bounds if b[1] > b[0]],
+                "stage3": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
+                "s_out": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
+                "frame": torch.empty(frame_host.shape, dtype=frame_host.dtype, device=dev),
+                "audio": torch.empty(audio_host.shape, dtype=torch.float32, device=dev),
+                "copy_stream": torch.cuda.Stream(device=dev),
+                "ev_small": torch.cuda.Event(), "ev": [torch.cuda.Event() for _ in bounds],
+            }
+        main = torch.cuda.current_stream(dev)
+        cs = st["copy_stream"]
+        cs.wait_stream(main)                                   # the previous call's kernels are done with the staging buffers
+        with torch.cuda.stream(cs):
+            st["frame"].copy_(frame_host, non_blocking=True)
+            st["audio"].copy_(audio_host, non_blocking=True)
+            st["ev_small"].record(cs)
+            for (lo, hi), ev in zip(st["bounds"], st["ev"]):
+                st["stage3"][lo:hi].copy_(stage3_host[lo:hi], non_blocking=True)
+                ev.record(cs)
+        vm = self.video_model.video_model
+        main.wait_event(st["ev_small"])
+        tok, n_clips = vm.t_former.tokens(st["frame"])
+        fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=dev)
+        self.audio_model.au_head.tokens_into(st["audio"], st["audio"].shape[1], n_clips, out=fused, ld_out=256)
+        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        out21, dec = self.au_head.logits21_(fused, n_clips, True)
+        if out_host is not None:
+            out_host.copy_(out21, non_blocking=True)
+        if dec_host is not None:
+            dec_host.copy_(dec, non_blocking=True)
+        for (lo, hi), ev in zip(st["bounds"], st["ev"]):
+            main.wait_event(ev)
+            vm.s_former.sformer(st["stage3"][lo:hi], out=st["s_out"][lo:hi])
+        return st["s_out"], out21, dec
+
     # -- loss helpers (models/avformer.py:108-123) ------------------------------------------------
     def get_au_loss(self, y_pred, y_true):
         return self.loss_AU(y_pred[:, :12], y_true)

@@ -176,7 +176,8 @@ def attention_fwd(qkv: torch.Tensor, n_seq: int, n_tok: int, heads: int, dim_hea
 # ------------------------------------------------------------------------------------------------
 # a6 / a7 / a8 / a9 / a11 / a12
 # ------------------------------------------------------------------------------------------------
-def sformer_fwd(fmap: torch.Tensor, pos: torch.Tensor, packed: PackedStack, heads: int, dim_head: int, mlp_dim: int) -> torch.Tensor:
+def sformer_fwd(fmap: torch.Tensor, pos: torch.Tensor, packed: PackedStack, heads: int, dim_head: int, mlp_dim: int,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """models/vformer.py:245-259 on a stage-3 map [F, C, H, W] (fp32 or bf16, NCHW-contiguous)."""
     fmap = _cuda(fmap, "fmap").contiguous()
     F_, C, H, W = fmap.shape
@@ -184,7 +185,10 @@ def sformer_fwd(fmap: torch.Tensor, pos: torch.Tensor, packed: PackedStack, head
     L = _lib.lib()
     need = L.avf_sformer_workspace_bytes(ctypes.byref(shape), packed.mode)
     ws = workspace(need, fmap.device)
-    out = torch.empty_like(fmap)
+    if out is None:
+        out = torch.empty_like(fmap)
+    elif out.shape != fmap.shape or out.dtype != fmap.dtype or not out.is_contiguous():
+        raise ValueError("sformer_fwd: `out` must be a contiguous tensor with the shape and dtype of the input map")
     check(L.avf_sformer_fwd(packed.mode, _io_mode(fmap), ctypes.byref(shape), packed.array, _ptr(_f32c(pos)), _ptr(fmap), _ptr(out),
                             _ptr(ws), ws.numel(), _stream()), "sformer_fwd")
     return out

@@ -88,8 +88,8 @@ class ResFormer(nn.Module):
         x = self.maxpool(self.relu(self.bn1(self.conv1(frames))))
         return self.layer3(self.layer2(self.layer1(x)))
 
-    def sformer(self, fmap):
-        """The hot-path region: [F,256,7,7] -> [F,256,7,7]."""
+    def sformer(self, fmap, out=None):
+        """The hot-path region: [F,256,7,7] -> [F,256,7,7] (``out``: optional preallocated destination, inference only)."""
         st = self.spatial_transformer
         n_tok = fmap.shape[2] * fmap.shape[3]
         if n_tok > self.pos_embedding.shape[1]:
@@ -97,7 +97,7 @@ class ResFormer(nn.Module):
         if needs_grad(st, fmap, self.pos_embedding) or st.dropout_state()[0] > 0.0:
             from .autograd import SFormerFn
             return SFormerFn.apply(fmap, self.pos_embedding, st, *st.param_list())
-        return AF.sformer_fwd(fmap, self.pos_embedding[0, :n_tok], st.packed(), st.heads, st.dim_head, st.mlp_dim)
+        return AF.sformer_fwd(fmap, self.pos_embedding[0, :n_tok], st.packed(), st.heads, st.dim_head, st.mlp_dim, out=out)
 
     def forward(self, x):
         b, t, c, h, w = x.shape

@@ -226,3 +226,21 @@ def test_larger_batch_against_oracle_and_idempotence():
     assert _maxerr(s1, ref["sformer_out"]) < 0.2
     _, l3 = run(torch.tensor([5, 17, 3]))
     assert _maxerr(l3, l1[[5, 17, 3]]) < 1e-5
+
+
+def test_hot_path_from_host_matches_device_path():
+    """The overlapped end-to-end entry (chunked H2D on a copy stream, kernels waiting per chunk) returns exactly what the
+    device-resident call returns, also when called back to back on changing inputs and with ragged chunking."""
+    T, B, seed = 16, 7, 41
+    m = _model(seed, T, "bf16")
+    out_host = torch.empty((B, 21), dtype=torch.float32).pin_memory()
+    dec_host = torch.empty((B, 12), dtype=torch.int32).pin_memory()
+    with torch.no_grad():
+        for it in range(3):
+            stage3, frame, audio = O.synth_hot_path_inputs(seed + it, B, T)
+            h = (stage3.bfloat16().pin_memory(), frame.bfloat16().pin_memory(), audio.pin_memory())
+            s_ref, o_ref, d_ref = m.hot_path(h[0].cuda(), h[1].cuda(), h[2].cuda(), want_decisions=True)
+            s_out, o, d = m.hot_path_from_host(*h, out_host, dec_host, chunks=3)
+            torch.cuda.synchronize()
+            assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
+            assert torch.equal(out_host, o_ref.cpu()) and torch.equal(dec_host, d_ref.cpu())
