@@ -198,19 +198,22 @@ int avf_gemm(int mode, int trans_a, int trans_b, const void* a, int32_t lda, con
  * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted).
  * dropout_p > 0 applies nn.Dropout at the reference's three sites per layer (after to_out, after GELU, after net.3;
  * models/heads.py:216,194,197) with a stateless counter-based mask derived from dropout_seed: the backward call must be given
- * the same (p, seed) and regenerates the masks instead of storing them.  avf_dropout_mask writes the scaled mask
+ * the same (p, seed, salt) and regenerates the masks instead of storing them.  dropout_salt (optional) points to one DEVICE
+ * uint32 that is hashed into the seed when the kernels start: a captured CUDA graph gets fresh masks on every replay by
+ * changing that word between replays.  avf_dropout_mask writes the scaled mask
  * (0 or 1/(1-p)) of one site (0 = to_out [rows, dim], 1 = GELU [rows, mlp_dim], 2 = net.3 [rows, dim]) for tests. */
 size_t avf_encoder_tape_bytes(const avf_stack_shape* s, int mode);
 size_t avf_encoder_bwd_workspace_bytes(const avf_stack_shape* s, int mode);
 int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
                                 const float* x, int32_t ld_x, float* out, int32_t ld_out,
-                                void* tape, size_t tape_bytes, float dropout_p, uint64_t dropout_seed, void* stream);
+                                void* tape, size_t tape_bytes, float dropout_p, uint64_t dropout_seed,
+                                const uint32_t* dropout_salt, void* stream);
 int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
                           const void* tape, size_t tape_bytes, float* dx, int32_t ld_dx,
                           const avf_layer_grads* grads, void* workspace, size_t workspace_bytes,
-                          float dropout_p, uint64_t dropout_seed, void* stream);
-int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, int32_t layer, int32_t site, int32_t rows, int32_t cols,
-                     float* out, void* stream);
+                          float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt, void* stream);
+int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt, int32_t layer, int32_t site,
+                     int32_t rows, int32_t cols, float* out, void* stream);
 
 /* Building blocks of the backward pass (exposed for tests). */
 /* out[c] = sum_r x[r, c]; x is fp32 or bf16 per in_mode with row stride ld (elements). */

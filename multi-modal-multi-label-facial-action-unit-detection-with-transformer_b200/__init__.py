@@ -13,6 +13,7 @@ from . import _lib
 from . import functional
 from . import autograd
 from . import optim
+from . import graphs
 from ._lib import build
 from .audio import AudioModel
 from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, load_pretrain
@@ -20,10 +21,11 @@ from .encoder import GELU, Attention, FeedForward, PreNorm, Residual, Transforme
 from .heads import AU_former, former_AU_head, tformer_AU_head
 from .loss import AULoss
 from .optim import FusedAdam
+from .graphs import GraphedHotPath, GraphedTrainStep
 from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
 
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "AudioModel", "FusedAdam", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]

@@ -71,10 +71,16 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 struct DropSpec {
   uint32_t seed = 0, thresh = 0;     // thresh = round(p * 2^32); 0 disables
   float scale = 1.f;                 // 1 / (1 - p)
+  const uint32_t* salt = nullptr;    // optional DEVICE word xor-ed into the seed at kernel start: lets a captured CUDA graph
+                                     // draw fresh masks on every replay (the host bumps / a graph node increments the word)
 };
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return h;
+}
+__device__ __forceinline__ DropSpec drop_resolve(DropSpec d) {      // once per thread, before the first drop_factor
+  if (d.thresh != 0 && d.salt != nullptr) d.seed ^= mix32(__ldg(d.salt));
+  return d;
 }
 __device__ __forceinline__ float drop_factor(const DropSpec& d, uint32_t idx) {
   return mix32(idx * 0x9E3779B1u ^ d.seed) >= d.thresh ? d.scale : 0.f;

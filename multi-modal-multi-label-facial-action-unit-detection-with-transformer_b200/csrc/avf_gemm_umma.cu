@@ -225,6 +225,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;             // which half of the tile's columns
     constexpr int HALF_COLS = BN / 2;
+    drop = drop_resolve(drop);
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int split = tile / mn_tiles, mn = tile - split * mn_tiles;

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __re
   __shared__ float Ws[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  drop = drop_resolve(drop);
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += 16) {
 #pragma unroll

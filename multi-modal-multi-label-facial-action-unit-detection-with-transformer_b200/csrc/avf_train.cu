@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             int rows_per_block, DropSpec drop_in, DropSpec drop_out) {
   constexpr int DIM = 128 * VEC;
   __shared__ float red[8][DIM];
+  drop_in = drop_resolve(drop_in);
+  drop_out = drop_resolve(drop_out);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float4 ag[VEC], ab[VEC], ad[VEC], gm[VEC];
@@ -164,10 +166,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 template <typename OutT>
 __global__ void __launch_bounds__(256) masked_copy_kernel(const float* __restrict__ x, OutT* __restrict__ y, size_t n, DropSpec drop) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  drop = drop_resolve(drop);
   if (i < n) y[i] = from_f32<OutT>(x[i] * drop_factor(drop, uint32_t(i)));
 }
 __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, size_t n, DropSpec drop) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  drop = drop_resolve(drop);
   if (i < n) out[i] = drop_factor(drop, uint32_t(i));
 }
 

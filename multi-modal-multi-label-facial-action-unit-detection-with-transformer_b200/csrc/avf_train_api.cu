@@ -67,9 +67,10 @@ int gemm(int mode, int ta, int tb, const void* a, int lda, const void* b, int ld
 }
 
 // Dropout site (layer, 0 = after to_out, 1 = after GELU, 2 = after net.3): models/heads.py:216,194,197
-static DropSpec drop_site(float p, uint64_t seed, int layer, int site) {
+static DropSpec drop_site(float p, uint64_t seed, const uint32_t* salt, int layer, int site) {
   DropSpec d;
   if (!(p > 0.f)) return d;
+  d.salt = salt;
   d.seed = mix32(uint32_t(seed) ^ mix32(uint32_t(seed >> 32) + 0x9E3779B9u * uint32_t(layer * 3 + site + 1)));
   const double t = double(p) * 4294967296.0;
   d.thresh = t >= 4294967295.0 ? 4294967295u : uint32_t(t);
@@ -86,7 +87,7 @@ static int copy_rows(float* dst, int ld_dst, const float* src, int ld_src, int r
 // forward with tape:  the residual stream walks x_in(0) -> x_mid(0) -> x_in(1) -> ... -> out
 // ---------------------------------------------------------------------------------------------
 static int encoder_fwd_train(int mode, const avf_stack_shape* s, const avf_layer_weights* L, const float* x, int ld_x, float* out, int ld_out,
-                             void* tape, size_t tape_bytes, float p_drop, uint64_t seed, cudaStream_t st) {
+                             void* tape, size_t tape_bytes, float p_drop, uint64_t seed, const uint32_t* salt, cudaStream_t st) {
   int e = check_train_shape(s);
   if (e) return e;
   AVF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, AVF_EINVAL, "dropout p=%f", p_drop);
@@ -107,14 +108,14 @@ static int encoder_fwd_train(int mode, const avf_stack_shape* s, const avf_layer
     if ((e = gemm(mode, 0, 0, t.xn1, D, W.w_qkv, D, nullptr, nullptr, 0, nullptr, 0, t.qkv, 3 * I, mode, R, 3 * I, D, 0, nullptr, 0, st))) return e;
     if ((e = attention_small(mode, t.qkv, t.o, s->n_seq, s->n_tok, s->heads, s->dim_head, st))) return e;
     if ((e = gemm(mode, 0, 0, t.o, I, W.w_out, I, W.b_out, t.x_in, D, nullptr, 0, t.x_mid, D, AVF_FP32, R, D, I, AVF_EPI_BIAS | AVF_EPI_RESIDUAL,
-                  nullptr, 0, st, drop_site(p_drop, seed, l, 0))))
+                  nullptr, 0, st, drop_site(p_drop, seed, salt, l, 0))))
       return e;
     if ((e = layernorm(mode, t.x_mid, D, W.ln2_gamma, W.ln2_beta, t.xn2, R, D, st))) return e;
     if ((e = gemm(mode, 0, 0, t.xn2, D, W.w_ff1, D, W.b_ff1, nullptr, 0, t.hpre, M, t.g, M, mode, R, M, D,
-                  AVF_EPI_BIAS | AVF_EPI_SAVE_PRE | AVF_EPI_GELU, nullptr, 0, st, drop_site(p_drop, seed, l, 1))))
+                  AVF_EPI_BIAS | AVF_EPI_SAVE_PRE | AVF_EPI_GELU, nullptr, 0, st, drop_site(p_drop, seed, salt, l, 1))))
       return e;
     if ((e = gemm(mode, 0, 0, t.g, M, W.w_ff2, M, W.b_ff2, t.x_mid, D, nullptr, 0, next, ld_next, AVF_FP32, R, D, M,
-                  AVF_EPI_BIAS | AVF_EPI_RESIDUAL, nullptr, 0, st, drop_site(p_drop, seed, l, 2))))
+                  AVF_EPI_BIAS | AVF_EPI_RESIDUAL, nullptr, 0, st, drop_site(p_drop, seed, salt, l, 2))))
       return e;
   }
   return 0;
@@ -157,7 +158,7 @@ static BwdWs carve_bwd_ws(const avf_stack_shape* s, int mode, void* base) {
 }
 
 static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* L, const void* tape, size_t tape_bytes, float* dx, int ld_dx,
-                       const avf_layer_grads* G, void* ws, size_t ws_bytes, float p_drop, uint64_t seed, cudaStream_t st) {
+                       const avf_layer_grads* G, void* ws, size_t ws_bytes, float p_drop, uint64_t seed, const uint32_t* salt, cudaStream_t st) {
   int e = check_train_shape(s);
   if (e) return e;
   AVF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, AVF_EINVAL, "dropout p=%f", p_drop);
@@ -175,7 +176,7 @@ static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weigh
   const void* dyb = dx;
   int ld_dyb = ld_dx;
   if (mode == AVF_BF16 || dropping) {
-    if ((e = masked_copy(dx, w.dyb, mode, R, D, drop_site(p_drop, seed, s->depth - 1, 2), st))) return e;
+    if ((e = masked_copy(dx, w.dyb, mode, R, D, drop_site(p_drop, seed, salt, s->depth - 1, 2), st))) return e;
     dyb = w.dyb;
     ld_dyb = D;
   }
@@ -187,13 +188,13 @@ static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weigh
     // ---- MLP sub-layer:  y = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2 ---------------------------------------
     if (g.w_ff2 && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.g, M, nullptr, nullptr, 0, nullptr, 0, g.w_ff2, M, AVF_FP32, D, M, R, 0, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, dyb, ld_dyb, W.w_ff2, M, nullptr, nullptr, 0, t.hpre, M, w.big, M, mode, R, M, D, AVF_EPI_DGELU, nullptr, 0, st,
-                  drop_site(p_drop, seed, l, 1))))
+                  drop_site(p_drop, seed, salt, l, 1))))
       return e;
     if (g.w_ff1 && (e = gemm(mode, 1, 1, w.big, M, t.xn2, D, nullptr, nullptr, 0, nullptr, 0, g.w_ff1, D, AVF_FP32, M, D, R, 0, w.red, w.red_bytes, st))) return e;
     if (g.b_ff1 && (e = colsum(mode, w.big, M, R, M, g.b_ff1, 0.f, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, w.big, M, W.w_ff1, D, nullptr, nullptr, 0, nullptr, 0, w.dxn, D, AVF_FP32, R, D, M, 0, nullptr, 0, st))) return e;
     if ((e = layernorm_bwd(t.x_mid, D, W.ln2_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln2_gamma, g.ln2_beta, g.b_ff2, 0.f, R, D, w.red, w.red_bytes, st,
-                           drop_site(p_drop, seed, l, 2), drop_site(p_drop, seed, l, 0))))
+                           drop_site(p_drop, seed, salt, l, 2), drop_site(p_drop, seed, salt, l, 0))))
       return e;
     // ---- attention sub-layer:  x_mid = x_in + Wo attn(Wqkv LN1(x_in)) + bo -----------------------------------
     if (g.w_out && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.o, I, nullptr, nullptr, 0, nullptr, 0, g.w_out, I, AVF_FP32, D, I, R, 0, w.red, w.red_bytes, st))) return e;
@@ -202,7 +203,7 @@ static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weigh
     if (g.w_qkv && (e = gemm(mode, 1, 1, w.big, 3 * I, t.xn1, D, nullptr, nullptr, 0, nullptr, 0, g.w_qkv, D, AVF_FP32, 3 * I, D, R, 0, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, w.big, 3 * I, W.w_qkv, D, nullptr, nullptr, 0, nullptr, 0, w.dxn, D, AVF_FP32, R, D, 3 * I, 0, nullptr, 0, st))) return e;
     if ((e = layernorm_bwd(t.x_in, D, W.ln1_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln1_gamma, g.ln1_beta, g.b_out, 0.f, R, D, w.red, w.red_bytes, st,
-                           drop_site(p_drop, seed, l, 0), l > 0 ? drop_site(p_drop, seed, l - 1, 2) : DropSpec{})))
+                           drop_site(p_drop, seed, salt, l, 0), l > 0 ? drop_site(p_drop, seed, salt, l - 1, 2) : DropSpec{})))
       return e;
   }
   return 0;
@@ -235,26 +236,28 @@ size_t avf_encoder_bwd_workspace_bytes(const avf_stack_shape* s, int mode) {
 }
 
 int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_layer_weights* layers, const float* x, int32_t ld_x, float* out,
-                                int32_t ld_out, void* tape, size_t tape_bytes, float dropout_p, uint64_t dropout_seed, void* stream) {
+                                int32_t ld_out, void* tape, size_t tape_bytes, float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt,
+                                void* stream) {
   int e = require_device_train();
   if (e) return e;
-  return encoder_fwd_train(mode, s, layers, x, ld_x, out, ld_out, tape, tape_bytes, dropout_p, dropout_seed, static_cast<cudaStream_t>(stream));
+  return encoder_fwd_train(mode, s, layers, x, ld_x, out, ld_out, tape, tape_bytes, dropout_p, dropout_seed, dropout_salt, static_cast<cudaStream_t>(stream));
 }
 
 int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers, const void* tape, size_t tape_bytes, float* dx,
                           int32_t ld_dx, const avf_layer_grads* grads, void* workspace, size_t workspace_bytes, float dropout_p,
-                          uint64_t dropout_seed, void* stream) {
+                          uint64_t dropout_seed, const uint32_t* dropout_salt, void* stream) {
   int e = require_device_train();
   if (e) return e;
-  return encoder_bwd(mode, s, layers, tape, tape_bytes, dx, ld_dx, grads, workspace, workspace_bytes, dropout_p, dropout_seed,
+  return encoder_bwd(mode, s, layers, tape, tape_bytes, dx, ld_dx, grads, workspace, workspace_bytes, dropout_p, dropout_seed, dropout_salt,
                      static_cast<cudaStream_t>(stream));
 }
 
-int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, int32_t layer, int32_t site, int32_t rows, int32_t cols, float* out, void* stream) {
+int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt, int32_t layer, int32_t site, int32_t rows,
+                     int32_t cols, float* out, void* stream) {
   int e = require_device_train();
   if (e) return e;
   AVF_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f && site >= 0 && site < 3 && layer >= 0, AVF_EINVAL, "dropout_mask: p=%f layer=%d site=%d", dropout_p, layer, site);
-  return dropout_mask(out, rows, cols, drop_site(dropout_p, dropout_seed, layer, site), static_cast<cudaStream_t>(stream));
+  return dropout_mask(out, rows, cols, drop_site(dropout_p, dropout_seed, dropout_salt, layer, site), static_cast<cudaStream_t>(stream));
 }
 
 size_t avf_gemm_workspace_bytes(int mode, int trans_a, int trans_b, int32_t m, int32_t n, int32_t k) {

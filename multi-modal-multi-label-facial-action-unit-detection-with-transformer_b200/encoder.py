@@ -124,6 +124,7 @@ class Transformer(nn.Module):
             for _ in range(depth)])
         self.precision: Optional[str] = None       # None -> default_precision()
         self.fixed_dropout_seed: Optional[int] = None
+        self.dropout_salt: Optional[torch.Tensor] = None
         self._packed: Optional[AF.PackedStack] = None
 
     # -- weights -------------------------------------------------------------------------------
@@ -151,23 +152,24 @@ class Transformer(nn.Module):
         return [lw[n] for lw in self._layer_tensors() for n in names]
 
     def dropout_state(self):
-        """(p, seed) of the next training forward: p = 0 in eval(); the seed is drawn from torch's default generator so that
-        torch.manual_seed makes runs reproducible.  ``fixed_dropout_seed`` (tests) pins it."""
+        """(p, seed, salt) of the next training forward: p = 0 in eval(); the seed is drawn from torch's default generator so
+        that torch.manual_seed makes runs reproducible.  ``fixed_dropout_seed`` (tests) pins it.  ``dropout_salt`` is an optional
+        one-element int32 CUDA tensor hashed into the seed on the device: graphs.GraphedTrainStep bumps it between replays."""
         if not self.training or self.dropout <= 0.0:
-            return 0.0, 0
+            return 0.0, 0, None
         seed = self.fixed_dropout_seed
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        return float(self.dropout), seed
+        return float(self.dropout), seed, self.dropout_salt
 
     # -- forward -------------------------------------------------------------------------------
     def forward_(self, x2d: torch.Tensor, n_seq: int, n_tok: int, out: Optional[torch.Tensor] = None, ld_out: int = 0) -> torch.Tensor:
         """Inference kernels, in place on an fp32 residual stream [n_seq*n_tok, dim].  In train() mode with dropout > 0 (a
         frozen sub-model inside a training loop, models/avformer.py:78-85 + train.py:327) the tape-keeping kernels run instead,
         because they are the ones that apply dropout."""
-        p, seed = self.dropout_state()
+        p, seed, salt = self.dropout_state()
         if p > 0.0:
-            y, _ = AF.encoder_stack_fwd_train(x2d, self.packed(), self.shape(n_seq, n_tok), p, seed)
+            y, _ = AF.encoder_stack_fwd_train(x2d, self.packed(), self.shape(n_seq, n_tok), p, seed, salt)
             if out is None:
                 x2d.copy_(y)
                 return x2d

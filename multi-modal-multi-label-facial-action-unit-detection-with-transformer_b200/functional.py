@@ -334,7 +334,8 @@ def attention_bwd(qkv: torch.Tensor, dout: torch.Tensor, n_seq: int, n_tok: int,
     return dqkv
 
 
-def encoder_stack_fwd_train(x: torch.Tensor, packed: PackedStack, shape: StackShape, dropout_p: float = 0.0, dropout_seed: int = 0):
+def encoder_stack_fwd_train(x: torch.Tensor, packed: PackedStack, shape: StackShape, dropout_p: float = 0.0, dropout_seed: int = 0,
+                            dropout_salt: Optional[torch.Tensor] = None):
     """Forward of a whole stack that keeps the activations the backward needs.  x [n_seq*n_tok, dim] fp32 is left
     untouched; returns (y, tape).  dropout_p > 0 applies the reference's three dropout sites per layer with masks derived from
     dropout_seed (give the same pair to encoder_stack_bwd_)."""
@@ -345,12 +346,12 @@ def encoder_stack_fwd_train(x: torch.Tensor, packed: PackedStack, shape: StackSh
     tape = torch.empty(L.avf_encoder_tape_bytes(ctypes.byref(shape), packed.mode), dtype=torch.uint8, device=x.device)
     y = torch.empty((x.shape[0], shape.dim), dtype=torch.float32, device=x.device)
     check(L.avf_encoder_stack_fwd_train(packed.mode, ctypes.byref(shape), packed.array, _ptr(x), x.stride(0), _ptr(y), shape.dim, _ptr(tape),
-                                        tape.numel(), float(dropout_p), int(dropout_seed), _stream()), "encoder_stack_fwd_train")
+                                        tape.numel(), float(dropout_p), int(dropout_seed), _ptr(dropout_salt), _stream()), "encoder_stack_fwd_train")
     return y, tape
 
 
 def encoder_stack_bwd_(dx: torch.Tensor, packed: PackedStack, shape: StackShape, tape: torch.Tensor, want: Sequence[bool],
-                       dropout_p: float = 0.0, dropout_seed: int = 0):
+                       dropout_p: float = 0.0, dropout_seed: int = 0, dropout_salt: Optional[torch.Tensor] = None):
     """dx [rows, dim] fp32 dense: dL/dy on entry, dL/dx on return.  ``want`` has 11*depth flags in avf_layer_weights
     order; returns the matching list of fp32 gradient tensors (None where not wanted)."""
     from ._lib import LayerGrads
@@ -366,7 +367,7 @@ def encoder_stack_bwd_(dx: torch.Tensor, packed: PackedStack, shape: StackShape,
     L = _lib.lib()
     ws = workspace(L.avf_encoder_bwd_workspace_bytes(ctypes.byref(shape), packed.mode), dx.device)
     check(L.avf_encoder_stack_bwd(packed.mode, ctypes.byref(shape), packed.array, _ptr(tape), tape.numel(), _ptr(dx), dx.stride(0), arr, _ptr(ws),
-                                  ws.numel(), float(dropout_p), int(dropout_seed), _stream()), "encoder_stack_bwd")
+                                  ws.numel(), float(dropout_p), int(dropout_seed), _ptr(dropout_salt), _stream()), "encoder_stack_bwd")
     return dx, grads
 
 
@@ -439,8 +440,10 @@ def adam_step_(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
                                    int(decoupled), grad_scale, _stream()), "adam_step")
 
 
-def dropout_mask(dropout_p: float, dropout_seed: int, layer: int, site: int, rows: int, cols: int, device) -> torch.Tensor:
+def dropout_mask(dropout_p: float, dropout_seed: int, layer: int, site: int, rows: int, cols: int, device,
+                 dropout_salt: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The scaled keep-mask (0 or 1/(1-p)) the kernels apply at one dropout site (0 to_out, 1 GELU, 2 net.3) of one layer."""
     out = torch.empty((rows, cols), dtype=torch.float32, device=device)
-    check(_lib.lib().avf_dropout_mask(float(dropout_p), int(dropout_seed), layer, site, rows, cols, _ptr(out), _stream()), "dropout_mask")
+    check(_lib.lib().avf_dropout_mask(float(dropout_p), int(dropout_seed), _ptr(dropout_salt), layer, site, rows, cols, _ptr(out), _stream()),
+          "dropout_mask")
     return out

@@ -1,0 +1,124 @@
+"""CUDA-graph front ends of the hot path.
+
+The hot path is a chain of ~60 (inference) / ~400 (training step) small launches behind one large persistent kernel; on a
+B200 the launch gaps and the Python/ctypes enqueue cost are comparable to the kernels themselves.  Capturing the chain once
+and replaying it removes both, and lets independent branches (the audio AU_former next to the video chain) run on parallel
+graph branches.  No tracing compiler is involved: the captured work is exactly the library's kernels.
+
+    GraphedHotPath(model, stage3, frame, audio)      inference: replay(stage3, frame, audio) -> (sformer_out, out21, decisions)
+    GraphedTrainStep(model, optimizer, ...)          zero_grad + forward + AULoss + backward in one graph, then FusedAdam.step()
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .encoder import Transformer
+
+
+def _side_warmup(fn, iters: int = 3) -> None:
+    """Warm-up on a side stream (allocations, lazy kernel attributes, weight packing) as torch.cuda.graph requires."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(iters):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+
+
+class GraphedHotPath:
+    """model.hot_path(...) captured for fixed input shapes.  Inputs are copied into static buffers (device-to-device or
+    host-to-device), outputs are the graph's static tensors (valid until the next replay)."""
+
+    def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor):
+        if model.training:
+            raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
+        self.model = model
+        self.stage3, self.frame = stage3.clone(), frame.clone()
+        self.audio = audio.float().clone()
+        self.side = torch.cuda.Stream()
+        with torch.no_grad():
+            _side_warmup(self._run)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._run()
+
+    def _run(self):
+        m = self.model
+        vm = m.video_model.video_model
+        cur = torch.cuda.current_stream()
+        n_clips = self.frame.numel() // (vm.t_former.num_patches * vm.t_former.dim)
+        fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=self.frame.device)
+        # branch: the audio AU_former is independent of everything up to the fusion head
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            m.audio_model.au_head.tokens_into(self.audio, self.audio.shape[1], n_clips, out=fused, ld_out=256)
+        tok, _ = vm.t_former.tokens(self.frame)
+        m.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        cur.wait_stream(self.side)
+        out21, dec = m.au_head.logits21_(fused, n_clips, True)
+        s_out = vm.s_former.sformer(self.stage3)
+        return s_out, out21, dec
+
+    def replay(self, stage3: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None, audio: Optional[torch.Tensor] = None):
+        if stage3 is not None and stage3.data_ptr() != self.stage3.data_ptr():
+            self.stage3.copy_(stage3, non_blocking=True)
+        if frame is not None and frame.data_ptr() != self.frame.data_ptr():
+            self.frame.copy_(frame, non_blocking=True)
+        if audio is not None and audio.data_ptr() != self.audio.data_ptr():
+            self.audio.copy_(audio, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+class GraphedTrainStep:
+    """One training step of the hot path (train.py:206-236 on the transformer stack) as a single graph replay:
+
+        zero_grad -> hot_path_train -> AULoss (+ optional gradient of the SFormer output) -> backward      [captured]
+        FusedAdam.step()  (gradient all-reduce + one update kernel; bias corrections depend on the step number) [eager]
+
+    Dropout masks are drawn afresh on every replay through a device-side salt word (see avf_encoder_stack_fwd_train); the
+    weight re-packing (fp32 master -> bf16 operands) is part of the captured forward, so replays always see the parameters
+    the optimiser just wrote."""
+
+    def __init__(self, model, optimizer, stage3, frame, audio, labels, d_sformer_out: Optional[torch.Tensor] = None):
+        self.model, self.opt = model, optimizer
+        self.stage3 = stage3.detach().clone().requires_grad_(stage3.requires_grad)
+        self.frame = frame.detach().clone().requires_grad_(frame.requires_grad)
+        self.audio = audio.detach().float().clone().requires_grad_(audio.requires_grad)
+        self.labels = labels.detach().clone()
+        self.d_s = d_sformer_out.detach().clone() if d_sformer_out is not None else None
+        self.salt = torch.zeros(1, dtype=torch.int32, device=labels.device)
+        for mod in model.modules():
+            if isinstance(mod, Transformer):
+                mod.dropout_salt = self.salt
+        # eager steps first: they build the optimiser's flat buckets (p.grad become persistent views) and warm every kernel up
+        _side_warmup(lambda: (self._fwd_bwd(), self.opt.step()))
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+
+    def _fwd_bwd(self):
+        self.salt.add_(0x61C88647)                      # new dropout masks for this step (int32 wrap-around is fine)
+        self.opt.zero_grad()
+        for t in (self.stage3, self.frame, self.audio):
+            if t.grad is not None:
+                t.grad = None
+        s_out, out21 = self.model.hot_path_train(self.stage3, self.frame, self.audio)
+        loss = self.model.get_au_loss(out21, self.labels)
+        if self.d_s is not None and s_out.requires_grad:
+            torch.autograd.backward([loss, s_out], [None, self.d_s])
+        else:
+            loss.backward()
+        return loss.detach()
+
+    def step(self, stage3=None, frame=None, audio=None, labels=None):
+        with torch.no_grad():
+            for dst, src in ((self.stage3, stage3), (self.frame, frame), (self.audio, audio), (self.labels, labels)):
+                if src is not None and src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.opt.step()
+        return self.loss

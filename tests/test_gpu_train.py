@@ -385,3 +385,60 @@ def test_train_mode_model_uses_dropout_and_stays_finite():
     assert torch.equal(a, b) and not torch.equal(a, c)            # reproducible under torch.manual_seed, random otherwise
     m.get_au_loss(c, labels.cuda()).backward()
     assert all(torch.isfinite(q.grad).all() for q in m.au_head.parameters())
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graph front ends
+# ---------------------------------------------------------------------------------------------
+def test_graphed_hot_path_equals_eager():
+    T, B, seed = 16, 9, 61
+    m = _model(seed, T, "bf16").eval()
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    dev = (stage3.bfloat16().cuda(), frame.bfloat16().cuda(), audio.cuda())
+    with torch.no_grad():
+        g = A.GraphedHotPath(m, *dev)
+        for it in range(3):
+            s3, fr, au = O.synth_hot_path_inputs(seed + it, B, T)
+            dev = (s3.bfloat16().cuda(), fr.bfloat16().cuda(), au.cuda())
+            s_ref, o_ref, d_ref = m.hot_path(*dev, want_decisions=True)
+            s_out, o, d = g.replay(*dev)
+            torch.cuda.synchronize()
+            assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
+
+
+def test_graphed_train_step_follows_eager_training():
+    """Same data, same start: N graph replays + FusedAdam steps land on the parameters N eager steps land on (dropout off so
+    that both runs are deterministic), and with dropout on the replays draw different masks each step."""
+    T, B, seed = 8, 8, 71
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2].cuda()
+    ins = (stage3.cuda().requires_grad_(True), frame.cuda().requires_grad_(True), audio.cuda().requires_grad_(True))
+
+    def hot(m):
+        return [q for k, q in m.named_parameters() if not O.is_backbone_key(k)]
+
+    m1 = _model(seed, T, "bf16", dropout=0.0).train()
+    opt1 = A.FusedAdam(hot(m1), lr=5e-4, weight_decay=5e-5)
+    eager_losses = []
+    for _ in range(3 + 4):                         # GraphedTrainStep spends 3 warm-up steps before capture
+        opt1.zero_grad()
+        _, out21 = m1.hot_path_train(*ins)
+        loss = m1.get_au_loss(out21, labels)
+        loss.backward()
+        opt1.step()
+        eager_losses.append(loss.item())
+    m2 = _model(seed, T, "bf16", dropout=0.0).train()
+    opt2 = A.FusedAdam(hot(m2), lr=5e-4, weight_decay=5e-5)
+    g = A.GraphedTrainStep(m2, opt2, *ins, labels)
+    graph_losses = [g.step().item() for _ in range(4)]
+    assert np.allclose(graph_losses, eager_losses[3:], rtol=1e-5, atol=1e-6), (graph_losses, eager_losses)
+    n1, n2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    assert all(torch.equal(n1[k], n2[k]) for k in n1 if not O.is_backbone_key(k))
+    bn1, bn2 = m1.video_model.au_head.AU_BN1, m2.video_model.au_head.AU_BN1
+    assert torch.equal(bn1.running_mean, bn2.running_mean) and int(bn2.num_batches_tracked) == 7
+    # dropout: fresh masks per replay
+    m3 = _model(seed, T, "bf16").train()
+    opt3 = A.FusedAdam(hot(m3), lr=0.0)            # lr 0: parameters frozen, so only the masks can change the loss
+    g3 = A.GraphedTrainStep(m3, opt3, *ins, labels)
+    ls = [g3.step().item() for _ in range(4)]
+    assert len(set(ls)) == 4 and all(np.isfinite(ls)), ls
