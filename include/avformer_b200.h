@@ -41,7 +41,8 @@ enum { AVF_EINVAL = -1, AVF_ENODEVICE = -2, AVF_EWORKSPACE = -3, AVF_EUNSUPPORTE
 /* epilogue flags of avf_linear_fwd */
 enum { AVF_EPI_BIAS = 1, AVF_EPI_GELU = 2, AVF_EPI_RESIDUAL = 4, AVF_EPI_DGELU = 8 /* x gelu'(aux), training */,
        AVF_EPI_SAVE_PRE = 16 /* store the pre-GELU value (after bias) to aux, training */,
-       AVF_EPI_DROPOUT = 32 /* dropout mask after bias/GELU, before the residual add (internal: needs a seed) */ };
+       AVF_EPI_DROPOUT = 32 /* dropout mask after bias/GELU, before the residual add (internal: needs a seed) */,
+       AVF_EPI_ACCUMULATE = 64 /* C += result (wgrad form: gradient accumulation straight into p.grad) */ };
 
 /* One pre-LN encoder layer (models/heads.py:246-250).  Weight matrices are [out, in] row-major
  * exactly as nn.Linear stores them; `w_dtype` says whether they are fp32 or bf16 copies
@@ -195,7 +196,8 @@ int avf_gemm(int mode, int trans_a, int trans_b, const void* a, int32_t lda, con
 
 /* Encoder stack, forward with an activation tape (x is NOT modified; the result goes to out, row stride ld_out)
  * and backward.  dx [n_seq*n_tok, dim] dense fp32 holds the gradient wrt the stack output on entry and the gradient
- * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted).
+ * wrt its input on return; grads[depth] receives the parameter gradients (NULL: none wanted); with accumulate != 0 they are
+ * ADDED to the buffers (which then are the optimiser's gradient bucket itself) instead of overwriting them.
  * dropout_p > 0 applies nn.Dropout at the reference's three sites per layer (after to_out, after GELU, after net.3;
  * models/heads.py:216,194,197) with a stateless counter-based mask derived from dropout_seed: the backward call must be given
  * the same (p, seed, salt) and regenerates the masks instead of storing them.  dropout_salt (optional) points to one DEVICE
@@ -210,7 +212,7 @@ int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_la
                                 const uint32_t* dropout_salt, void* stream);
 int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers,
                           const void* tape, size_t tape_bytes, float* dx, int32_t ld_dx,
-                          const avf_layer_grads* grads, void* workspace, size_t workspace_bytes,
+                          const avf_layer_grads* grads, int accumulate, void* workspace, size_t workspace_bytes,
                           float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt, void* stream);
 int avf_dropout_mask(float dropout_p, uint64_t dropout_seed, const uint32_t* dropout_salt, int32_t layer, int32_t site,
                      int32_t rows, int32_t cols, float* out, void* stream);

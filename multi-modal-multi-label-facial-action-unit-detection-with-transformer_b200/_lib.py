@@ -85,7 +85,7 @@ SIGNATURES = {
     "avf_encoder_stack_fwd_train": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _i32, _c_p, _i32,
                                                    _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
     "avf_encoder_stack_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _sz, _c_p, _i32,
-                                             ctypes.POINTER(LayerGrads), _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
+                                             ctypes.POINTER(LayerGrads), ctypes.c_int, _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
     "avf_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),

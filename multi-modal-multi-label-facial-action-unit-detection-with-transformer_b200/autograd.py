@@ -2,7 +2,8 @@
 ``autograd.Function`` whose forward runs the tape-keeping CUDA forward and whose backward runs the hand-written
 backward kernels, so ``loss.backward()`` in the reference's training loop works unchanged and the conv backbones
 (plain torch) receive their input gradients.  Parameters are passed as Function inputs so that autograd accumulates
-the returned gradients into ``p.grad`` like for any other module.
+the returned gradients into ``p.grad`` like for any other module; when ``p.grad`` already exists as an fp32 buffer
+(FusedAdam keeps them as views of its flat gradient bucket) the encoder kernels accumulate straight into it instead.
 
 No arithmetic happens in torch here: tensors are allocated, viewed and handed to libavformer_b200.so.
 """
@@ -28,14 +29,14 @@ class EncoderStackFn(torch.autograd.Function):
         shape = tr.shape(n_seq, n_tok)
         ctx.drop = tr.dropout_state()
         y, tape = AF.encoder_stack_fwd_train(_f32_dense(x.detach()), packed, shape, *ctx.drop)
-        ctx.packed, ctx.shape_, ctx.tape = packed, shape, tape
+        ctx.packed, ctx.shape_, ctx.tape, ctx.params = packed, shape, tape, params
         return y
 
     @staticmethod
     def backward(ctx, dy):
         needs = ctx.needs_input_grad
         dx = _f32_dense(dy).clone()
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop)
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop, into=[p.grad for p in ctx.params])
         ctx.tape = None
         return (dx if needs[0] else None, None, None, None, *grads)
 
@@ -52,6 +53,7 @@ class SFormerFn(torch.autograd.Function):
         ctx.drop = tr.dropout_state()
         y, tape = AF.encoder_stack_fwd_train(x, packed, shape, *ctx.drop)
         ctx.packed, ctx.shape_, ctx.tape, ctx.fshape, ctx.fdtype, ctx.pos_shape = packed, shape, tape, (F_, C, H, W), fmap.dtype, pos.shape
+        ctx.params = params
         return AF.sformer_tokens_unpack(y, (F_, C, H, W), fmap.dtype)
 
     @staticmethod
@@ -59,7 +61,7 @@ class SFormerFn(torch.autograd.Function):
         needs = ctx.needs_input_grad
         F_, C, H, W = ctx.fshape
         dx = AF.sformer_tokens_pack(dout, None)
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]), *ctx.drop)
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]), *ctx.drop, into=[p.grad for p in ctx.params])
         ctx.tape = None
         dpos = None
         if needs[1]:

@@ -330,10 +330,15 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
 }
 
 namespace {
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out,
+                                                            int accumulate) {
   const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = *reinterpret_cast<const float4*>(part + i);
+  if (accumulate) {
+    const float4 v = *reinterpret_cast<const float4*>(out + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
   for (int s = 1; s < splits; ++s) {
     const float4 v = *reinterpret_cast<const float4*>(part + size_t(s) * n + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -361,7 +366,8 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
   const int m_tiles = ceil_div(m, BM), sms = sm_count();
   if (trans_a && trans_b) {
     // wgrad: few output tiles, long reduction -> split K so that every SM has a tile
-    AVF_REQUIRE(c_mode == AVF_FP32 && flags == 0, AVF_EUNSUPPORTED, "linear(bf16): the TN form writes plain fp32");
+    const bool accumulate = (flags & AVF_EPI_ACCUMULATE) != 0;
+    AVF_REQUIRE(c_mode == AVF_FP32 && (flags & ~AVF_EPI_ACCUMULATE) == 0, AVF_EUNSUPPORTED, "linear(bf16): the TN form writes (or accumulates into) plain fp32");
     const int bn = n % 128 == 0 ? 128 : 64;
     const int mn_tiles = m_tiles * (n / bn), kblocks = ceil_div(k, BK);
     int splits = std::max(1, std::min(kblocks, sms / std::max(1, mn_tiles)));
@@ -371,7 +377,7 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
     float* out = static_cast<float*>(c);
     float* part = out;
     size_t stride = 0;
-    if (splits > 1) {
+    if (splits > 1 || accumulate) {
       AVF_REQUIRE(ldc == n, AVF_EINVAL, "linear(bf16): split-K output must be dense (ldc=%d n=%d)", ldc, n);
       AVF_REQUIRE(ws != nullptr && ws_bytes >= elems * splits * sizeof(float), AVF_EWORKSPACE,
                   "linear(bf16): split-K workspace too small: %zu < %zu bytes", ws_bytes, elems * splits * sizeof(float));
@@ -381,8 +387,8 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
     int e = bn == 128 ? launch_gemm<128, 6, float, true, true>(a, lda, w, ldw, part, ldc, nullptr, nullptr, 0, m, n, k, 0, nullptr, 0, splits, stride, stream)
                       : launch_gemm<64, 8, float, true, true>(a, lda, w, ldw, part, ldc, nullptr, nullptr, 0, m, n, k, 0, nullptr, 0, splits, stride, stream);
     if (e) return e;
-    if (splits > 1) {
-      splitk_reduce_kernel<<<unsigned((elems / 4 + 255) / 256), 256, 0, stream>>>(part, splits, elems, out);
+    if (splits > 1 || accumulate) {
+      splitk_reduce_kernel<<<unsigned((elems / 4 + 255) / 256), 256, 0, stream>>>(part, splits, elems, out, accumulate ? 1 : 0);
       AVF_LAUNCH_CHECK("splitk_reduce_kernel");
     }
     return 0;
@@ -413,7 +419,7 @@ size_t gemm_umma_workspace_bytes(int m, int n, int k) {       // for the TN (wgr
   const int sms = sm_count(), bn = n % 128 == 0 ? 128 : 64;
   const int mn_tiles = ceil_div(m, BM) * (n / bn), kblocks = ceil_div(k, BK);
   const int splits = std::max(1, std::min(kblocks, sms / std::max(1, mn_tiles)));
-  return splits > 1 ? size_t(m) * n * splits * sizeof(float) : 0;
+  return size_t(m) * n * splits * sizeof(float);      // splits == 1 still needs one tile set when the result is accumulated
 }
 
 // C = epi(A W^T) with bf16 operands; c_mode selects fp32 / bf16 output.

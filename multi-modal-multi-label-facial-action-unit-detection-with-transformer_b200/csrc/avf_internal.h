@@ -55,6 +55,7 @@ int adam_step(float* p, const float* g, float* m, float* v, void* shadow, size_t
 
 // avf_attention_mma.cu
 int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+int attention_bwd_mma_bf16(const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
 // avf_layer_fused.cu: whole encoder stack in one persistent tcgen05 kernel (dim 256, 8 heads x 32)
 bool encoder_fused_supported(const avf_stack_shape* s);

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __re
       if (flags & AVF_EPI_GELU) v = gelu_tanh<false>(v);
       if (flags & AVF_EPI_DROPOUT) v *= drop_factor(drop, uint32_t(r) * uint32_t(N) + uint32_t(c));
       if (flags & AVF_EPI_RESIDUAL) v += res[size_t(r) * ld_res + c];
+      if (flags & AVF_EPI_ACCUMULATE) v += to_f32<OutT>(C[size_t(r) * ldc + c]);
       C[size_t(r) * ldc + c] = from_f32<OutT>(v);
     }
   }
@@ -235,7 +236,7 @@ int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, 
              float* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, cudaStream_t st, DropSpec drop) {
   AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
   AVF_REQUIRE(!(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE)) || aux != nullptr, AVF_EINVAL, "linear(fp32): DGELU / SAVE_PRE epilogues need the pre-activation buffer");
-  if (!trans_a && !trans_b && ldw == k && !(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE | AVF_EPI_DROPOUT)) && k % 16 == 0 && lda % 4 == 0)
+  if (!trans_a && !trans_b && ldw == k && !(flags & (AVF_EPI_DGELU | AVF_EPI_SAVE_PRE | AVF_EPI_DROPOUT | AVF_EPI_ACCUMULATE)) && k % 16 == 0 && lda % 4 == 0)
     return linear_f32(a, lda, w, bias, res, ld_res, c, ldc, c_mode, m, n, k, flags, st);
   dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
   const long a_rs = trans_a ? 1 : lda, a_cs = trans_a ? lda : 1, w_rs = trans_b ? 1 : ldw, w_cs = trans_b ? ldw : 1;

@@ -39,16 +39,36 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
   }
 }
 
-// out_q[c] = beta * out_q[c] + sum_b part[b, q * cols + c] for up to three outputs packed side by side in `part`
+// out_q[c] = beta * out_q[c] + sum_b part[b, q * cols + c] for up to three outputs packed side by side in `part`.
+// 32 columns x 8 partial-row lanes per block: the chunk loop is split 8 ways and unrolled so that the (L2-latency bound)
+// loads overlap; the order of the additions is fixed.
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, int n_out,
                                                            float* o0, float* o1, float* o2, float beta) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cols * n_out) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int idx = blockIdx.x * 32 + tx, width = cols * n_out;
+  float a = 0.f;
+  if (idx < width) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = ty;
+    for (; b + 24 < chunks; b += 32) {
+      a0 += part[size_t(b) * width + idx];
+      a1 += part[size_t(b + 8) * width + idx];
+      a2 += part[size_t(b + 16) * width + idx];
+      a3 += part[size_t(b + 24) * width + idx];
+    }
+    for (; b < chunks; b += 8) a0 += part[size_t(b) * width + idx];
+    a = (a0 + a1) + (a2 + a3);
+  }
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty != 0 || idx >= width) return;
+  a = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a += red[i][tx];
   const int q = idx / cols, c = idx - q * cols;
   float* o = q == 0 ? o0 : (q == 1 ? o1 : o2);
   if (o == nullptr) return;
-  float a = 0.f;
-  for (int b = 0; b < chunks; ++b) a += part[size_t(b) * cols * n_out + idx];
   o[c] = beta != 0.f ? beta * o[c] + a : a;
 }
 
@@ -441,12 +461,12 @@ int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out
   if (in_mode == AVF_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
   else colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
   AVF_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<ceil_div(cols, 256), 256, 0, st>>>(part, int(grid.y), cols, 1, out, nullptr, nullptr, beta);
+  colsum_final_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(part, int(grid.y), cols, 1, out, nullptr, nullptr, beta);
   AVF_LAUNCH_CHECK("colsum_final_kernel");
   return 0;
 }
 
-static int ln_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 8), 296)); }
+static int ln_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 8), 148)); }
 size_t layernorm_bwd_workspace_bytes(int rows, int dim) { return size_t(ln_bwd_blocks(rows)) * 3 * dim * sizeof(float); }
 
 int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, int dxb_mode, float* dgamma,
@@ -469,7 +489,7 @@ int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn
   }
   AVF_LAUNCH_CHECK("layernorm_bwd_kernel");
   if (dgamma || dbeta || dbias) {
-    colsum_final_kernel<<<ceil_div(3 * dim, 256), 256, 0, st>>>(part, grid, dim, 3, dgamma, dbeta, dbias, beta_acc);
+    colsum_final_kernel<<<ceil_div(3 * dim, 32), 256, 0, st>>>(part, grid, dim, 3, dgamma, dbeta, dbias, beta_acc);
     AVF_LAUNCH_CHECK("colsum_final_kernel");
   }
   return 0;
@@ -511,9 +531,7 @@ static int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, i
 int attention_bwd(int io_mode, const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st) {
   AVF_REQUIRE(n_seq > 0 && n_tok > 0 && n_tok <= 64 && heads > 0, AVF_EINVAL, "attention_bwd: n_seq=%d n_tok=%d heads=%d", n_seq, n_tok, heads);
   AVF_REQUIRE(dim_head == 32 || dim_head == 64, AVF_EUNSUPPORTED, "attention_bwd: dim_head=%d (supported: 32, 64)", dim_head);
-  if (io_mode == AVF_BF16)
-    return dim_head == 32 ? launch_attention_bwd<__nv_bfloat16, 32>(qkv, dout, dqkv, n_seq, n_tok, heads, st)
-                          : launch_attention_bwd<__nv_bfloat16, 64>(qkv, dout, dqkv, n_seq, n_tok, heads, st);
+  if (io_mode == AVF_BF16) return attention_bwd_mma_bf16(qkv, dout, dqkv, n_seq, n_tok, heads, dim_head, st);      // tensor cores
   return dim_head == 32 ? launch_attention_bwd<float, 32>(qkv, dout, dqkv, n_seq, n_tok, heads, st)
                         : launch_attention_bwd<float, 64>(qkv, dout, dqkv, n_seq, n_tok, heads, st);
 }

@@ -158,11 +158,14 @@ static BwdWs carve_bwd_ws(const avf_stack_shape* s, int mode, void* base) {
 }
 
 static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* L, const void* tape, size_t tape_bytes, float* dx, int ld_dx,
-                       const avf_layer_grads* G, void* ws, size_t ws_bytes, float p_drop, uint64_t seed, const uint32_t* salt, cudaStream_t st) {
+                       const avf_layer_grads* G, int accumulate, void* ws, size_t ws_bytes, float p_drop, uint64_t seed, const uint32_t* salt,
+                       cudaStream_t st) {
   int e = check_train_shape(s);
   if (e) return e;
   AVF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, AVF_EINVAL, "dropout p=%f", p_drop);
   const bool dropping = p_drop > 0.f;
+  const int wg = accumulate ? AVF_EPI_ACCUMULATE : 0;       // wgrad epilogue
+  const float beta = accumulate ? 1.f : 0.f;
   AVF_REQUIRE(mode == AVF_BF16 || mode == AVF_FP32, AVF_EINVAL, "mode=%d", mode);
   AVF_REQUIRE(L && tape && dx && ws, AVF_EINVAL, "encoder_stack_bwd: null pointer");
   AVF_REQUIRE(tape_bytes >= layer_tape_bytes(s, mode) * s->depth, AVF_EWORKSPACE, "tape too small");
@@ -186,23 +189,23 @@ static int encoder_bwd(int mode, const avf_stack_shape* s, const avf_layer_weigh
     const avf_layer_grads& g = G ? G[l] : none;
     const LayerTape t = carve_tape(s, mode, const_cast<void*>(tape), l);
     // ---- MLP sub-layer:  y = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2 ---------------------------------------
-    if (g.w_ff2 && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.g, M, nullptr, nullptr, 0, nullptr, 0, g.w_ff2, M, AVF_FP32, D, M, R, 0, w.red, w.red_bytes, st))) return e;
+    if (g.w_ff2 && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.g, M, nullptr, nullptr, 0, nullptr, 0, g.w_ff2, M, AVF_FP32, D, M, R, wg, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, dyb, ld_dyb, W.w_ff2, M, nullptr, nullptr, 0, t.hpre, M, w.big, M, mode, R, M, D, AVF_EPI_DGELU, nullptr, 0, st,
                   drop_site(p_drop, seed, salt, l, 1))))
       return e;
-    if (g.w_ff1 && (e = gemm(mode, 1, 1, w.big, M, t.xn2, D, nullptr, nullptr, 0, nullptr, 0, g.w_ff1, D, AVF_FP32, M, D, R, 0, w.red, w.red_bytes, st))) return e;
-    if (g.b_ff1 && (e = colsum(mode, w.big, M, R, M, g.b_ff1, 0.f, w.red, w.red_bytes, st))) return e;
+    if (g.w_ff1 && (e = gemm(mode, 1, 1, w.big, M, t.xn2, D, nullptr, nullptr, 0, nullptr, 0, g.w_ff1, D, AVF_FP32, M, D, R, wg, w.red, w.red_bytes, st))) return e;
+    if (g.b_ff1 && (e = colsum(mode, w.big, M, R, M, g.b_ff1, beta, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, w.big, M, W.w_ff1, D, nullptr, nullptr, 0, nullptr, 0, w.dxn, D, AVF_FP32, R, D, M, 0, nullptr, 0, st))) return e;
-    if ((e = layernorm_bwd(t.x_mid, D, W.ln2_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln2_gamma, g.ln2_beta, g.b_ff2, 0.f, R, D, w.red, w.red_bytes, st,
+    if ((e = layernorm_bwd(t.x_mid, D, W.ln2_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln2_gamma, g.ln2_beta, g.b_ff2, beta, R, D, w.red, w.red_bytes, st,
                            drop_site(p_drop, seed, salt, l, 2), drop_site(p_drop, seed, salt, l, 0))))
       return e;
     // ---- attention sub-layer:  x_mid = x_in + Wo attn(Wqkv LN1(x_in)) + bo -----------------------------------
-    if (g.w_out && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.o, I, nullptr, nullptr, 0, nullptr, 0, g.w_out, I, AVF_FP32, D, I, R, 0, w.red, w.red_bytes, st))) return e;
+    if (g.w_out && (e = gemm(mode, 1, 1, dyb, ld_dyb, t.o, I, nullptr, nullptr, 0, nullptr, 0, g.w_out, I, AVF_FP32, D, I, R, wg, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, dyb, ld_dyb, W.w_out, I, nullptr, nullptr, 0, nullptr, 0, w.dob, I, mode, R, I, D, 0, nullptr, 0, st))) return e;
     if ((e = attention_bwd(mode, t.qkv, w.dob, w.big, s->n_seq, s->n_tok, s->heads, s->dim_head, st))) return e;
-    if (g.w_qkv && (e = gemm(mode, 1, 1, w.big, 3 * I, t.xn1, D, nullptr, nullptr, 0, nullptr, 0, g.w_qkv, D, AVF_FP32, 3 * I, D, R, 0, w.red, w.red_bytes, st))) return e;
+    if (g.w_qkv && (e = gemm(mode, 1, 1, w.big, 3 * I, t.xn1, D, nullptr, nullptr, 0, nullptr, 0, g.w_qkv, D, AVF_FP32, 3 * I, D, R, wg, w.red, w.red_bytes, st))) return e;
     if ((e = gemm(mode, 0, 1, w.big, 3 * I, W.w_qkv, D, nullptr, nullptr, 0, nullptr, 0, w.dxn, D, AVF_FP32, R, D, 3 * I, 0, nullptr, 0, st))) return e;
-    if ((e = layernorm_bwd(t.x_in, D, W.ln1_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln1_gamma, g.ln1_beta, g.b_out, 0.f, R, D, w.red, w.red_bytes, st,
+    if ((e = layernorm_bwd(t.x_in, D, W.ln1_gamma, w.dxn, dx, ld_dx, dxb_out, mode, g.ln1_gamma, g.ln1_beta, g.b_out, beta, R, D, w.red, w.red_bytes, st,
                            drop_site(p_drop, seed, salt, l, 0), l > 0 ? drop_site(p_drop, seed, salt, l - 1, 2) : DropSpec{})))
       return e;
   }
@@ -244,11 +247,11 @@ int avf_encoder_stack_fwd_train(int mode, const avf_stack_shape* s, const avf_la
 }
 
 int avf_encoder_stack_bwd(int mode, const avf_stack_shape* s, const avf_layer_weights* layers, const void* tape, size_t tape_bytes, float* dx,
-                          int32_t ld_dx, const avf_layer_grads* grads, void* workspace, size_t workspace_bytes, float dropout_p,
+                          int32_t ld_dx, const avf_layer_grads* grads, int accumulate, void* workspace, size_t workspace_bytes, float dropout_p,
                           uint64_t dropout_seed, const uint32_t* dropout_salt, void* stream) {
   int e = require_device_train();
   if (e) return e;
-  return encoder_bwd(mode, s, layers, tape, tape_bytes, dx, ld_dx, grads, workspace, workspace_bytes, dropout_p, dropout_seed, dropout_salt,
+  return encoder_bwd(mode, s, layers, tape, tape_bytes, dx, ld_dx, grads, accumulate, workspace, workspace_bytes, dropout_p, dropout_seed, dropout_salt,
                      static_cast<cudaStream_t>(stream));
 }
 

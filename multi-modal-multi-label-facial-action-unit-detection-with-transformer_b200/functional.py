@@ -351,23 +351,34 @@ def encoder_stack_fwd_train(x: torch.Tensor, packed: PackedStack, shape: StackSh
 
 
 def encoder_stack_bwd_(dx: torch.Tensor, packed: PackedStack, shape: StackShape, tape: torch.Tensor, want: Sequence[bool],
-                       dropout_p: float = 0.0, dropout_seed: int = 0, dropout_salt: Optional[torch.Tensor] = None):
+                       dropout_p: float = 0.0, dropout_seed: int = 0, dropout_salt: Optional[torch.Tensor] = None,
+                       into: Optional[Sequence[Optional[torch.Tensor]]] = None):
     """dx [rows, dim] fp32 dense: dL/dy on entry, dL/dx on return.  ``want`` has 11*depth flags in avf_layer_weights
-    order; returns the matching list of fp32 gradient tensors (None where not wanted)."""
+    order; returns the matching list of fp32 gradient tensors (None where not wanted).
+
+    ``into`` (optional, same order): existing fp32 contiguous gradient buffers — typically the ``p.grad`` views of the
+    optimiser's flat bucket.  When every wanted gradient has one, the kernels ACCUMULATE straight into them and the returned
+    list holds None throughout (nothing left for autograd to add)."""
     from ._lib import LayerGrads
     names = [n for n, _ in LayerWeights._fields_]
+    n_par = packed.depth * len(names)
+    direct = into is not None and all((not want[i]) or (into[i] is not None and into[i].dtype == torch.float32 and into[i].is_contiguous()
+                                                         and into[i].is_cuda) for i in range(n_par))
     grads: List[Optional[torch.Tensor]] = []
     arr = (LayerGrads * packed.depth)()
     for l in range(packed.depth):
         for j, name in enumerate(names):
-            src = packed.sources[l * len(names) + j]
-            g = torch.empty(src.shape, dtype=torch.float32, device=dx.device) if want[l * len(names) + j] else None
-            grads.append(g)
+            i = l * len(names) + j
+            g = None
+            if want[i]:
+                g = into[i] if direct else torch.empty(packed.sources[i].shape, dtype=torch.float32, device=dx.device)
+            grads.append(None if direct else g)
             setattr(arr[l], name, g.data_ptr() if g is not None else None)
     L = _lib.lib()
     ws = workspace(L.avf_encoder_bwd_workspace_bytes(ctypes.byref(shape), packed.mode), dx.device)
-    check(L.avf_encoder_stack_bwd(packed.mode, ctypes.byref(shape), packed.array, _ptr(tape), tape.numel(), _ptr(dx), dx.stride(0), arr, _ptr(ws),
-                                  ws.numel(), float(dropout_p), int(dropout_seed), _ptr(dropout_salt), _stream()), "encoder_stack_bwd")
+    check(L.avf_encoder_stack_bwd(packed.mode, ctypes.byref(shape), packed.array, _ptr(tape), tape.numel(), _ptr(dx), dx.stride(0), arr,
+                                  1 if direct else 0, _ptr(ws), ws.numel(), float(dropout_p), int(dropout_seed), _ptr(dropout_salt), _stream()),
+          "encoder_stack_bwd")
     return dx, grads
 
 
