@@ -14,6 +14,7 @@ from . import functional
 from . import autograd
 from . import optim
 from . import graphs
+from . import dp
 from ._lib import build
 from .audio import AudioModel
 from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, load_pretrain
@@ -27,5 +28,5 @@ from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]

@@ -466,7 +466,7 @@ int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out
   return 0;
 }
 
-static int ln_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 8), 148)); }
+static int ln_bwd_blocks(int rows) { return std::max(1, std::min(ceil_div(rows, 8), 592)); }
 size_t layernorm_bwd_workspace_bytes(int rows, int dim) { return size_t(ln_bwd_blocks(rows)) * 3 * dim * sizeof(float); }
 
 int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn, float* dres, int ld_d, void* dxb, int dxb_mode, float* dgamma,
