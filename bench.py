@@ -311,12 +311,20 @@ def run_ours(args):
     if rank == 0:
         flops_sformer = B * T * FLOP_SFORMER_PER_FRAME
         if roof is None:
-            roof = {"kernel": "avf_sformer_fwd (all kernels of the SFormer region: pack, LN, 4 tcgen05 linears, attention, unpack)",
-                    "achieved": flops_sformer / (ms_sformer * 1e-3) / 1e12, "launches": None}
+            roof = {"kernel": "encoder_fused_kernel<0>: the whole SFormer region (NCHW->tokens +pos, LN, QKV, attention, out-proj, MLP, tokens->NCHW) "
+                              "as ONE persistent tcgen05 kernel, 1 launch per step, timed alone with CUDA events on its launch stream",
+                    "achieved": flops_sformer / (ms_sformer * 1e-3) / 1e12, "launches": 1}
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):        # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+                tj = json.load(open(tpath))
+                roof["traffic"] = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                roof["traffic_source"] = tj["source"]
+                roof["algorithmic_bytes"] = tj["algorithmic_bytes"]
         roofline = {"bound": "tensor", "achieved": roof["achieved"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": roof["achieved"] / peaks["bf16_tflops"], "traffic": roof.get("traffic"),
                     "kernel": roof["kernel"], "peak_source": f"{peaks['source']} (burst: kernel timed alone)",
-                    "algorithmic_flop_per_launch": flops_sformer}
+                    "algorithmic_flop_per_launch": flops_sformer, "traffic_source": roof.get("traffic_source"),
+                    "algorithmic_bytes_per_launch": roof.get("algorithmic_bytes"), "share_of_step": ms_sformer / ms_step}
         sample = 64
         cpu_v, cpu_t, cores = cpu_hot_path_clips_per_s(sample, repeats=3)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
