@@ -244,3 +244,30 @@ def test_hot_path_from_host_matches_device_path():
             torch.cuda.synchronize()
             assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
             assert torch.equal(out_host, o_ref.cpu()) and torch.equal(dec_host, d_ref.cpu())
+
+
+@pytest.mark.parametrize("B", [1, 2, 5, 33])
+def test_eval_sweep_shape_T32_decisions_and_f1(B):
+    """BASELINE config 5 (32-frame clips, batch 1..): logits within the bf16 tolerance of the oracle, and the 0.5-threshold
+    decisions / accuracy / per-AU F1 (metrics/accf1.py via the oracle) identical to the reference's wherever the reference
+    logit is not within the tolerance of the threshold."""
+    T, seed = 32, 500 + B
+    p = O.make_state_dict(seed, T, hot_path_only=True)
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2]
+    ref = O.hot_path_forward(stage3.double(), frame.double(), audio.double(), O.cast_params(p, torch.float64), T)
+    m = _model(seed, T, "bf16")
+    with torch.no_grad():
+        _, out21, dec = m.hot_path(stage3.bfloat16().cuda(), frame.bfloat16().cuda(), audio.cuda(), want_decisions=True)
+    # inputs were rounded to bf16 (the SFormer / TFormer feeds of the bench): compare against the oracle on the same rounded inputs
+    ref = O.hot_path_forward(stage3.bfloat16().double(), frame.bfloat16().double(), audio.double(), O.cast_params(p, torch.float64), T)
+    assert _maxerr(out21[:, :12], ref["logits"]) < BF16_ATOL
+    ref_dec = O.decisions(ref["logits"])
+    sure = (ref["logits"].abs() > BF16_ATOL).numpy()
+    got = dec.cpu().numpy()
+    assert np.array_equal(got[sure], ref_dec[sure])
+    assert np.array_equal(got, (out21[:, :12].cpu().numpy() > 0).astype(got.dtype))
+    if sure.all():
+        a0, f0, _ = O.multilabel_acc_f1(labels.numpy(), ref_dec, ignore_index=-1)
+        a1, f1, _ = O.multilabel_acc_f1(labels.numpy(), got.astype(np.int64), ignore_index=-1)
+        assert a0 == a1 and f0 == f1
