@@ -160,6 +160,12 @@ int avf_au_logits_fwd(const float* x, int32_t ld_x, const float* w_last, float* 
 int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels, const float* pos_weight,
                     float* loss_out, float* dlogits, int32_t n_clips, void* stream);
 
+/* MultiLabelAccF1 (metrics/accf1.py:45-77) without leaving the device: counts48 [12][4] (uint64, ACCUMULATED) += {TP, FP, FN, TN} per AU
+ * over the entries whose label != ignore; pred > threshold is the positive decision (logits: 0, i.e. round(sigmoid), train.py:155;
+ * 0/1 predictions: 0.5).  acc = sum(TP+TN) / sum(all), f1 = mean_i 2 TP_i / (2 TP_i + FP_i + FN_i); across ranks the 48 counters add. */
+int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
+                            uint64_t* counts48, int32_t n_rows, void* stream);
+
 /* ---- parameter preparation ------------------------------------------------------------------ */
 int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

@@ -21,6 +21,7 @@ from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, loa
 from .encoder import GELU, Attention, FeedForward, PreNorm, Residual, Transformer, default_precision, set_default_precision
 from .heads import AU_former, former_AU_head, tformer_AU_head
 from .loss import AULoss
+from .metrics import MultiLabelAccF1
 from .optim import FusedAdam
 from .graphs import GraphedHotPath, GraphedTrainStep
 from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
@@ -28,5 +29,5 @@ from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "MultiLabelAccF1", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]

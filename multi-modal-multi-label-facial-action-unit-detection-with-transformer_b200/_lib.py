@@ -73,6 +73,7 @@ SIGNATURES = {
                                                _c_p, _sz, _c_p]),
     "avf_au_logits_fwd": (ctypes.c_int, [_c_p, _i32, _c_p, _c_p, _c_p, _i32, _i32, _c_p]),
     "avf_au_bce_loss": (ctypes.c_int, [_c_p, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _c_p]),
+    "avf_au_confusion_update": (ctypes.c_int, [_c_p, _i32, ctypes.c_float, _c_p, _i32, ctypes.c_float, _c_p, _i32, _c_p]),
     "avf_cast_f32_to_bf16": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_cast_bf16_to_f32": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_add_row_periodic": (ctypes.c_int, [_c_p, _i32, _c_p, _i32, _i32, _i32, _c_p]),

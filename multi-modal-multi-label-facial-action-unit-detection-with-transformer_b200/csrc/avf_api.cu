@@ -290,6 +290,14 @@ int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels,
   return au_bce(logits, ld_logits, labels, pos_weight, loss_out, dlogits, n_clips, static_cast<cudaStream_t>(stream));
 }
 
+int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
+                            uint64_t* counts48, int32_t n_rows, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  return au_confusion(pred, ld_pred, threshold, labels, ld_labels, ignore, reinterpret_cast<unsigned long long*>(counts48), n_rows,
+                      static_cast<cudaStream_t>(stream));
+}
+
 int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream) {
   int e = require_device();
   if (e) return e;

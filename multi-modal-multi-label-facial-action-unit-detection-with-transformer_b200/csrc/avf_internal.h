@@ -21,6 +21,8 @@ int cast_f32_bf16(const float* s, void* d, size_t n, cudaStream_t st);
 int cast_bf16_f32(const void* s, float* d, size_t n, cudaStream_t st);
 int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* decisions, int n_clips, int dim, cudaStream_t st);
 int au_bce(const float* logits, int ld, const float* labels, const float* pw, float* loss_out, float* dlogits, int n_clips, cudaStream_t st);
+int au_confusion(const float* pred, int ld_pred, float thresh, const float* labels, int ld_lab, float ignore, unsigned long long* counts, int n_rows,
+                 cudaStream_t st);
 
 // avf_simt.cu
 int linear_f32(const float* a, int lda, const float* w, const float* bias, const float* res, int ld_res, void* c, int ldc,

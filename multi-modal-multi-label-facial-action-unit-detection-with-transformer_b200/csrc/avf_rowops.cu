@@ -1,6 +1,8 @@
 // Memory-bound pieces of the AVFormer hot path as vectorised, coalesced warp-shuffle kernels:
 // LayerNorm, BatchNorm(eval) rows, SFormer NCHW<->token transposes (+pos), TFormer cls/pos embed,
 // casts, the 12 per-AU dot products + decisions, and the pos-weighted BCE (+gradient).
+#include <algorithm>
+
 #include "avf_common.cuh"
 
 namespace avf {
@@ -230,6 +232,27 @@ __global__ void __launch_bounds__(256) au_bce_kernel(const float* __restrict__ l
   }
 }
 
+// Per-AU confusion counters for MultiLabelAccF1 (metrics/accf1.py:45-77): counts[au][0..3] += {TP, FP, FN, TN} over the entries
+// whose label is not `ignore`.  pred > thresh is the positive decision (logits: thresh 0 == round(sigmoid(x)), train.py:155;
+// already-rounded predictions: thresh 0.5).  Integer atomics: the result does not depend on the order of the additions.
+__global__ void __launch_bounds__(256) au_confusion_kernel(const float* __restrict__ pred, int ld_pred, float thresh,
+                                                           const float* __restrict__ labels, int ld_lab, float ignore,
+                                                           unsigned long long* __restrict__ counts, int n_rows) {
+  __shared__ unsigned int sc[12][4];
+  if (threadIdx.x < 48) sc[threadIdx.x / 4][threadIdx.x % 4] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * 12; i += gridDim.x * blockDim.x) {
+    const int r = i / 12, c = i - r * 12;
+    const float y = labels[size_t(r) * ld_lab + c];
+    if (y == ignore) continue;
+    const bool p = pred[size_t(r) * ld_pred + c] > thresh, t = y == 1.0f;
+    atomicAdd(&sc[c][p ? (t ? 0 : 1) : (t ? 2 : 3)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 48 && sc[threadIdx.x / 4][threadIdx.x % 4] != 0)
+    atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x / 4][threadIdx.x % 4]);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -336,6 +359,14 @@ int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* 
   AVF_REQUIRE(n_clips > 0 && dim % 4 == 0 && ld_x % 4 == 0, AVF_EINVAL, "au_logits: n_clips=%d dim=%d", n_clips, dim);
   au_logits_kernel<<<ceil_div(n_clips * 12, 8), 256, 0, st>>>(x, ld_x, w_last, out21, decisions, n_clips, dim);
   AVF_LAUNCH_CHECK("au_logits_kernel");
+  return 0;
+}
+
+int au_confusion(const float* pred, int ld_pred, float thresh, const float* labels, int ld_lab, float ignore, unsigned long long* counts, int n_rows,
+                 cudaStream_t st) {
+  AVF_REQUIRE(n_rows > 0 && pred && labels && counts, AVF_EINVAL, "au_confusion_update: n_rows=%d", n_rows);
+  au_confusion_kernel<<<std::min(ceil_div(n_rows * 12, 256), 296), 256, 0, st>>>(pred, ld_pred, thresh, labels, ld_lab, ignore, counts, n_rows);
+  AVF_LAUNCH_CHECK("au_confusion_kernel");
   return 0;
 }
 

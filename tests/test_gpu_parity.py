@@ -271,3 +271,35 @@ def test_eval_sweep_shape_T32_decisions_and_f1(B):
         a0, f0, _ = O.multilabel_acc_f1(labels.numpy(), ref_dec, ignore_index=-1)
         a1, f1, _ = O.multilabel_acc_f1(labels.numpy(), got.astype(np.int64), ignore_index=-1)
         assert a0 == a1 and f0 == f1
+
+
+def test_multilabel_acc_f1_counters_match_reference_metric():
+    """metrics/accf1.py:45-77 from 48 device-side counters: same accuracy / mean binary F1 as the oracle restatement (and as
+    sklearn, which the reference calls), with per-entry ignore labels, an AU without positives, several updates and both entry points."""
+    from sklearn.metrics import f1_score
+    torch.manual_seed(4)
+    metric = A.MultiLabelAccF1(ignore_index=-1)
+    all_true, all_pred = [], []
+    for n in (1, 37, 1000):
+        logits = torch.randn(n, 21, device="cuda") * 2
+        y = (torch.rand(n, 12, device="cuda") < 0.3).float()
+        y[torch.rand(n, 12, device="cuda") < 0.1] = -1.0             # unlabeled entries
+        y[:, 5] = torch.where(y[:, 5] == 1, torch.zeros_like(y[:, 5]), y[:, 5])     # AU 5 never positive
+        logits[:, 5] = -1.0
+        pred = O.decisions(logits[:, :12].cpu())
+        if n == 37:
+            metric.update(pred.astype(np.float32), y.cpu().numpy())   # the reference's call: rounded predictions, numpy
+        else:
+            metric.update_from_logits(logits, y)
+        all_true.append(y.cpu().numpy())
+        all_pred.append(pred)
+    yt, yp = np.vstack(all_true), np.vstack(all_pred)
+    acc, f1 = metric.get()
+    acc0, f10, _ = O.multilabel_acc_f1(yt, yp, ignore_index=-1)
+    assert abs(acc - acc0) < 1e-12 and abs(f1 - f10) < 1e-12
+    sk = np.mean([f1_score(yt[:, i][yt[:, i] != -1], yp[:, i][yt[:, i] != -1], average="binary", zero_division=0) for i in range(12)])
+    assert abs(f1 - sk) < 1e-12
+    c = metric.confusion()
+    assert c.sum() == int((yt != -1).sum()) and c[5, 0] == 0 and c[5, 1] == 0
+    metric.clear()
+    assert metric.confusion().sum() == 0
