@@ -15,7 +15,6 @@ from . import autograd
 from . import optim
 from . import graphs
 from . import dp
-from . import runner
 from ._lib import build
 from .audio import AudioModel
 from .avformer import AudioFormer, TwoStreamAuralVisualFormer, VisualFormer, load_pretrain
