@@ -24,10 +24,11 @@ from .loss import AULoss
 from .metrics import MultiLabelAccF1
 from .optim import FusedAdam
 from .graphs import GraphedHotPath, GraphedTrainStep
+from .inference import InferenceEngine
 from .video import BasicBlock, Dummy, ResFormer, TFormer, VideoModel
 
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "MultiLabelAccF1", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "MultiLabelAccF1", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "InferenceEngine", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]

@@ -303,3 +303,25 @@ def test_multilabel_acc_f1_counters_match_reference_metric():
     assert c.sum() == int((yt != -1).sum()) and c[5, 0] == 0 and c[5, 1] == 0
     metric.clear()
     assert metric.confusion().sum() == 0
+
+
+def test_inference_engine_matches_module_forward():
+    """Whole model through InferenceEngine (BN folded into channels_last convs, one CUDA graph per shape): fp32 backbones reproduce
+    model(x) up to the re-association of the fold; bf16 backbones (opt-in) stay within 0.25 on the logits and agree on every decision
+    whose fp32 logit is farther than that from the threshold; replays track changing inputs."""
+    T, B, seed = 8, 3, 208
+    m = _model(seed, T, "bf16")
+    eng32 = A.InferenceEngine(m, backbone_dtype=torch.float32)
+    eng16 = A.InferenceEngine(m, backbone_dtype=torch.bfloat16)
+    for it in range(2):
+        clip, audio, _ = O.synth_inputs(seed + it, B, T)
+        x = {"clip": clip.cuda(), "audio_features": audio.cuda(), "Index": torch.arange(B).cuda()}
+        with torch.no_grad():
+            ref = m(x)
+        o32 = eng32(x).clone()
+        o16 = eng16(x).clone()
+        assert o32.shape == (B, 21) and float(o32[:, 12:].abs().max()) == 0.0
+        assert _maxerr(o32, ref) < 5e-3, _maxerr(o32, ref)
+        assert _maxerr(o16, ref) < 0.25, _maxerr(o16, ref)
+        sure = (ref[:, :12].abs() > 0.25)
+        assert bool((((o16[:, :12] > 0) == (ref[:, :12] > 0)) | ~sure).all())
