@@ -67,43 +67,105 @@ __global__ void bn_rows_kernel(const float* __restrict__ x, int ld_x, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// SFormer token packing: fmap [F, dim, hw] -> x [F*hw, dim] + pos  (models/vformer.py:247-253)
-// One CTA per frame; the frame is read linearly (coalesced), transposed through padded smem and
-// written as full 4*dim-byte rows.
+// SFormer token packing: fmap [F, dim, hw] -> x [F*hw, dim] + pos  (models/vformer.py:247-253) and back (:257-259).
+// One frame per CTA iteration, staged in shared memory as fp32 in its NATURAL [dim][hw] order:
+//   * the NCHW side is moved with 16-byte vectors over the flat frame (fully coalesced);
+//   * the token side is moved one token row at a time, lane <-> channel: a warp instruction reads / writes 32 consecutive
+//     fp32 of a token row (128 B, coalesced) and touches tile[(c0 + lane) * hw + t] in shared memory — conflict-free
+//     whenever hw is odd (7x7 = 49: bank = (17 lane + t) mod 32), at most 2-way otherwise (pitch hw|1).
 // ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;      // 16-byte global access of 8 bf16 / 4 fp32
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { f[2 * q] = __uint_as_float(w[q] << 16); f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+
 template <typename InT>
 __global__ void __launch_bounds__(256) sformer_pack_kernel(const InT* __restrict__ fmap, const float* __restrict__ pos,
-                                                           float* __restrict__ x, int dim, int hw) {
-  extern __shared__ float tile[];               // [dim][hw + 1]
-  const int f = blockIdx.x, pitch = hw + 1;
-  const InT* src = fmap + size_t(f) * dim * hw;
-  for (int i = threadIdx.x; i < dim * hw; i += blockDim.x) {
-    const int c = i / hw, t = i - c * hw;
-    tile[c * pitch + t] = to_f32<InT>(src[i]);
-  }
-  __syncthreads();
-  float* dst = x + size_t(f) * hw * dim;
-  for (int i = threadIdx.x; i < dim * hw; i += blockDim.x) {
-    const int t = i / dim, c = i - t * dim;
-    dst[i] = tile[c * pitch + t] + (pos != nullptr ? __ldg(pos + i) : 0.f);
+                                                           float* __restrict__ x, int n_frames, int dim, int hw) {
+  extern __shared__ float tile[];               // [dim][pitch], pitch = hw | 1
+  constexpr int V = Vec16<InT>::N;
+  const int pitch = hw | 1, n = dim * hw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const InT* src = fmap + size_t(f) * n;
+    for (int i = threadIdx.x * V; i < n; i += blockDim.x * V) {          // n % V == 0 is checked by the launcher
+      float v[V];
+      Vec16<InT>::load(src + i, v);
+      if (pitch == hw) {                         // odd hw: the tile IS the flat frame -> 16-byte shared-memory stores
+#pragma unroll
+        for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(&tile[i + j]) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        int c = i / hw, t = i - c * hw;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          tile[c * pitch + t] = v[j];
+          if (++t == hw) { t = 0; ++c; }
+        }
+      }
+    }
+    __syncthreads();
+    float* dst = x + size_t(f) * n;
+    for (int t = warp; t < hw; t += 8) {
+      for (int c = lane; c < dim; c += 32) {
+        const float p = pos != nullptr ? __ldg(pos + t * dim + c) : 0.f;
+        dst[t * dim + c] = tile[c * pitch + t] + p;
+      }
+    }
+    __syncthreads();
   }
 }
 
 // x [F*hw, dim] -> fmap [F, dim, hw]   (models/vformer.py:257-259)
 template <typename OutT>
-__global__ void __launch_bounds__(256) sformer_unpack_kernel(const float* __restrict__ x, OutT* __restrict__ fmap, int dim, int hw) {
-  extern __shared__ float tile[];               // [hw][dim + 1]
-  const int f = blockIdx.x, pitch = dim + 1;
-  const float* src = x + size_t(f) * hw * dim;
-  for (int i = threadIdx.x; i < dim * hw; i += blockDim.x) {
-    const int t = i / dim, c = i - t * dim;
-    tile[t * pitch + c] = src[i];
-  }
-  __syncthreads();
-  OutT* dst = fmap + size_t(f) * dim * hw;
-  for (int i = threadIdx.x; i < dim * hw; i += blockDim.x) {
-    const int c = i / hw, t = i - c * hw;
-    dst[i] = from_f32<OutT>(tile[t * pitch + c]);
+__global__ void __launch_bounds__(256) sformer_unpack_kernel(const float* __restrict__ x, OutT* __restrict__ fmap, int n_frames, int dim, int hw) {
+  extern __shared__ float tile[];               // [dim][pitch]
+  constexpr int V = Vec16<OutT>::N;
+  const int pitch = hw | 1, n = dim * hw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const float* src = x + size_t(f) * n;
+    for (int t = warp; t < hw; t += 8)
+      for (int c = lane; c < dim; c += 32) tile[c * pitch + t] = src[t * dim + c];
+    __syncthreads();
+    OutT* dst = fmap + size_t(f) * n;
+    for (int i = threadIdx.x * V; i < n; i += blockDim.x * V) {
+      float v[V];
+      if (pitch == hw) {
+#pragma unroll
+        for (int j = 0; j < V; j += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(&tile[i + j]);
+          v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+        }
+      } else {
+        int c = i / hw, t = i - c * hw;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          v[j] = tile[c * pitch + t];
+          if (++t == hw) { t = 0; ++c; }
+        }
+      }
+      Vec16<OutT>::store(dst + i, v);
+    }
+    __syncthreads();
   }
 }
 
@@ -285,34 +347,47 @@ int bn_rows(int out_mode, const float* x, int ld_x, const float* g, const float*
   return 0;
 }
 
+static int sformer_grid(int n_frames, size_t smem) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = std::max(1, std::min(4, int((220 * 1024) / (smem + 1024))));
+  return std::min(n_frames, sms * per_sm);
+}
+
 int sformer_pack(int io_mode, const void* fmap, const float* pos, float* x, int n_frames, int dim, int hw, cudaStream_t st) {
   AVF_REQUIRE(n_frames > 0 && dim > 0 && hw > 0, AVF_EINVAL, "sformer_tokens_pack: empty input");
-  const size_t smem = size_t(dim) * (hw + 1) * 4;
+  const size_t smem = size_t(dim) * (hw | 1) * 4;
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "sformer_tokens_pack: frame of %d x %d does not fit shared memory", dim, hw);
+  AVF_REQUIRE((size_t(dim) * hw) % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15) == 0, AVF_EUNSUPPORTED,
+              "sformer_tokens_pack: frames must be 16-byte aligned multiples of 8 elements (dim=%d hw=%d)", dim, hw);
   static bool cfg = false;
   if (!cfg) {
     AVF_CUDA(cudaFuncSetAttribute(sformer_pack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVF_CUDA(cudaFuncSetAttribute(sformer_pack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg = true;
   }
-  if (io_mode == AVF_BF16) sformer_pack_kernel<__nv_bfloat16><<<n_frames, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(fmap), pos, x, dim, hw);
-  else sformer_pack_kernel<float><<<n_frames, 256, smem, st>>>(static_cast<const float*>(fmap), pos, x, dim, hw);
+  const int grid = sformer_grid(n_frames, smem);
+  if (io_mode == AVF_BF16) sformer_pack_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(fmap), pos, x, n_frames, dim, hw);
+  else sformer_pack_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(fmap), pos, x, n_frames, dim, hw);
   AVF_LAUNCH_CHECK("sformer_pack_kernel");
   return 0;
 }
 
 int sformer_unpack(int io_mode, const float* x, void* fmap, int n_frames, int dim, int hw, cudaStream_t st) {
   AVF_REQUIRE(n_frames > 0 && dim > 0 && hw > 0, AVF_EINVAL, "sformer_tokens_unpack: empty input");
-  const size_t smem = size_t(hw) * (dim + 1) * 4;
+  const size_t smem = size_t(dim) * (hw | 1) * 4;
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "sformer_tokens_unpack: frame of %d x %d does not fit shared memory", dim, hw);
+  AVF_REQUIRE((size_t(dim) * hw) % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15) == 0, AVF_EUNSUPPORTED,
+              "sformer_tokens_unpack: frames must be 16-byte aligned multiples of 8 elements (dim=%d hw=%d)", dim, hw);
   static bool cfg = false;
   if (!cfg) {
     AVF_CUDA(cudaFuncSetAttribute(sformer_unpack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVF_CUDA(cudaFuncSetAttribute(sformer_unpack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg = true;
   }
-  if (io_mode == AVF_BF16) sformer_unpack_kernel<__nv_bfloat16><<<n_frames, 256, smem, st>>>(x, static_cast<__nv_bfloat16*>(fmap), dim, hw);
-  else sformer_unpack_kernel<float><<<n_frames, 256, smem, st>>>(x, static_cast<float*>(fmap), dim, hw);
+  const int grid = sformer_grid(n_frames, smem);
+  if (io_mode == AVF_BF16) sformer_unpack_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, static_cast<__nv_bfloat16*>(fmap), n_frames, dim, hw);
+  else sformer_unpack_kernel<float><<<grid, 256, smem, st>>>(x, static_cast<float*>(fmap), n_frames, dim, hw);
   AVF_LAUNCH_CHECK("sformer_unpack_kernel");
   return 0;
 }

@@ -19,6 +19,58 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // column sums:  out[c] = beta * out[c] + sum_r x[r, c]          (fixed summation order)
 // ---------------------------------------------------------------------------------------------
+template <typename T> struct RowVec;       // 16-byte row fragment: 8 bf16 / 4 fp32
+template <> struct RowVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void add(const __nv_bfloat16* p, float (&a)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { a[2 * q] += __uint_as_float(w[q] << 16); a[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u); }
+  }
+};
+template <> struct RowVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void add(const float* p, float (&a)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+  }
+};
+
+// Vectorised partial sums: a warp covers 32 * N consecutive columns with one 16-byte load per lane and row; the 8 warps of
+// a block take every 8th row of the block's row chunk (two independent accumulator sets for memory-level parallelism).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __restrict__ x, size_t ld, int rows, int cols, int rows_per_chunk,
+                                                                 float* __restrict__ part) {
+  constexpr int N = RowVec<T>::N;
+  __shared__ float red[8][32 * N + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + lane) * N;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float a[N], b[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) a[j] = b[j] = 0.f;
+  if (col < cols) {
+    int r = r0 + warp;
+    for (; r + 8 < r1; r += 16) {
+      RowVec<T>::add(x + size_t(r) * ld + col, a);
+      RowVec<T>::add(x + size_t(r + 8) * ld + col, b);
+    }
+    if (r < r1) RowVec<T>::add(x + size_t(r) * ld + col, a);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) red[warp][lane * N + j] = a[j] + b[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * N; c += 256) {
+    const int gc = blockIdx.x * 32 * N + c;
+    if (gc >= cols) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    part[size_t(blockIdx.y) * cols + gc] = s;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, size_t ld, int rows, int cols, int rows_per_chunk,
                                                              float* __restrict__ part) {
@@ -102,13 +154,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     const float4* xp = reinterpret_cast<const float4*>(x + size_t(row) * ld_x);
     const float4* yp = reinterpret_cast<const float4*>(dyn + size_t(row) * DIM);
     float4* dp = reinterpret_cast<float4*>(dres + size_t(row) * ld_d);
-    float4 v[VEC], g[VEC];
+    float4 v[VEC], g[VEC], dy[VEC], rs[VEC];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
+    for (int i = 0; i < VEC; ++i) {          // all three streams of the row are requested before the first reduction
       v[i] = xp[lane + 32 * i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      dy[i] = yp[lane + 32 * i];
+      rs[i] = dp[lane + 32 * i];
     }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) * (1.0f / DIM);
     float ss = 0.f;
 #pragma unroll
@@ -120,7 +175,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 d = yp[lane + 32 * i];
+      const float4 d = dy[i];
       v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;       // xhat
       ag[i].x += d.x * v[i].x; ag[i].y += d.y * v[i].y; ag[i].z += d.z * v[i].z; ag[i].w += d.w * v[i].w;
       ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
@@ -132,7 +187,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     m2 = warp_sum(m2) * (1.0f / DIM);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 r = dp[lane + 32 * i];
+      const float4 r = rs[i];
       if (drop_in.thresh != 0) {      // bias gradient of a sub-layer whose output went through dropout: sum the masked gradient
         const uint32_t i0 = uint32_t(row) * DIM + (lane + 32 * i) * 4;
         ad[i].x += r.x * drop_factor(drop_in, i0); ad[i].y += r.y * drop_factor(drop_in, i0 + 1);
@@ -442,24 +497,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static int colsum_chunks(int rows, int cols) {
-  const int col_blocks = ceil_div(cols, 32);
-  int chunks = std::max(1, std::min(ceil_div(rows, 64), 592 / std::max(1, col_blocks)));
-  return chunks;
+static int colsum_chunks(int rows, int cols) {      // upper bound over both kernel variants (workspace sizing)
+  const int col_blocks = ceil_div(cols, 256);
+  return std::max(1, std::min(ceil_div(rows, 32), ceil_div(1184, std::max(1, col_blocks))));
 }
 
 size_t colsum_workspace_bytes(int rows, int cols) { return size_t(colsum_chunks(rows, cols)) * cols * sizeof(float); }
 
 int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out, float beta, void* ws, size_t ws_bytes, cudaStream_t st) {
   AVF_REQUIRE(rows > 0 && cols > 0 && x && out, AVF_EINVAL, "colsum: rows=%d cols=%d", rows, cols);
-  const int chunks = colsum_chunks(rows, cols);
+  const int vec = in_mode == AVF_BF16 ? 8 : 4, esz = in_mode == AVF_BF16 ? 2 : 4;
+  const bool vectorised = cols % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int col_blocks = ceil_div(cols, vectorised ? 32 * vec : 32);
+  const int chunks = std::max(1, std::min(colsum_chunks(rows, cols), std::min(ceil_div(rows, 32), ceil_div(1184, col_blocks))));
   AVF_REQUIRE(ws != nullptr && ws_bytes >= size_t(chunks) * cols * 4, AVF_EWORKSPACE, "colsum: workspace too small (%zu < %zu bytes)",
               ws_bytes, size_t(chunks) * cols * 4);
+  (void)esz;
   const int rpc = ceil_div(rows, chunks);
-  dim3 grid(ceil_div(cols, 32), ceil_div(rows, rpc));
+  dim3 grid(col_blocks, ceil_div(rows, rpc));
   float* part = static_cast<float*>(ws);
-  if (in_mode == AVF_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
-  else colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
+  if (vectorised) {
+    if (in_mode == AVF_BF16) colsum_partial_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
+    else colsum_partial_vec_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
+  } else {
+    if (in_mode == AVF_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
+    else colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
+  }
   AVF_LAUNCH_CHECK("colsum_partial_kernel");
   colsum_final_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(part, int(grid.y), cols, 1, out, nullptr, nullptr, beta);
   AVF_LAUNCH_CHECK("colsum_final_kernel");
