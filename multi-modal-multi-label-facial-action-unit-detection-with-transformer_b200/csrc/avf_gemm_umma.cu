@@ -45,7 +45,8 @@ struct GemmCfg {
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
                                                const float* __restrict__ bias, const float* res, int ld_res, int flags,
-                                               __nv_bfloat16* aux, int ld_aux, const DropSpec& drop, int n_total) {
+                                               __nv_bfloat16* aux, int ld_aux, const DropSpec& drop, int n_total,
+                                               const float4* pre_res = nullptr) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -94,7 +95,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
     const float* rp = res + size_t(row) * ld_res + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 r = *reinterpret_cast<const float4*>(rp + j);
+      const float4 r = pre_res != nullptr ? pre_res[j >> 2] : *reinterpret_cast<const float4*>(rp + j);
       f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
     }
   }
@@ -233,20 +234,47 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       OutT* Cs = C + size_t(split) * split_stride;
       const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
       const int row = m0 + q * 32 + lane;
-      mbar_wait(&acc_full[buf], aph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * BN + half * HALF_COLS;
-#pragma unroll 1
-      for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + uint32_t(c0), v);
-        tmem_ld_wait();
-        if (c0 + 32 >= HALF_COLS) {               // last chunk is in registers: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if constexpr (HALF_COLS <= 64) {
+        // Narrow tiles are epilogue-latency bound (K is short on this path): request the thread's residual fragment BEFORE
+        // waiting for the accumulator, so that the HBM/L2 round trip overlaps the main loop of this tile.
+        float4 pre[HALF_COLS / 4];
+        const bool want_res = (flags & AVF_EPI_RESIDUAL) && row < M;
+        if (want_res) {
+          const float4* rp = reinterpret_cast<const float4*>(res + size_t(row) * ld_res + n0 + half * HALF_COLS);
+#pragma unroll
+          for (int j = 0; j < HALF_COLS / 4; ++j) pre[j] = rp[j];
         }
-        if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N);
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + uint32_t(c0), v);
+          tmem_ld_wait();
+          if (c0 + 32 >= HALF_COLS) {             // last chunk is in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          if (row < M)
+            epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N, want_res ? &pre[c0 / 4] : nullptr);
+        }
+      } else {
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + uint32_t(c0), v);
+          tmem_ld_wait();
+          if (c0 + 32 >= HALF_COLS) {             // last chunk is in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N);
+        }
       }
     }
   }
