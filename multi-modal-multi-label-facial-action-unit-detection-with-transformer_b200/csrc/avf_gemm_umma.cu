@@ -424,7 +424,9 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
   AVF_REQUIRE(!trans_a, AVF_EUNSUPPORTED, "linear(bf16): transposed A is only implemented together with transposed B");
   // widest tile that still gives every SM at least two tiles; small problems get narrower tiles for parallelism
   int bn = 64;
-  if (n % 256 == 0 && m_tiles * (n / 256) >= 2 * sms) bn = 256;
+  // the wide tile halves the operand traffic per FLOP: bf16 outputs take it from 0.8 waves on, fp32 outputs (whose epilogue
+  // then moves 128 KB per tile without the residual prefetch) only when there are at least two waves
+  if (n % 256 == 0 && m_tiles * (n / 256) * 5 >= (c_mode == AVF_BF16 ? 4 : 10) * sms) bn = 256;
   else if (n % 128 == 0 && m_tiles * (n / 128) >= sms) bn = 128;
   else if (n % 128 == 0 && n / 128 * m_tiles >= sms / 2 && n >= 512) bn = 128;
 #define AVF_GEMM(BN_, ST_, BMN_)                                                                                                   \
