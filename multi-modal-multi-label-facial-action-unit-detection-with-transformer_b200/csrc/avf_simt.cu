@@ -162,27 +162,30 @@ __device__ __forceinline__ void store_frag(T* __restrict__ p, const float (&src)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int DH>
 __global__ void __launch_bounds__(DH == 32 ? 512 : 256) attention_small_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n_seq, int n_tok,
-                                                              int heads, int spb, float scale_log2e) {
+                                                              int heads, int spb, int hpb, float scale_log2e) {
   extern __shared__ uint8_t smem_attn[];
-  T* kv = reinterpret_cast<T*>(smem_attn);                // [spb][n_tok][2*inner]  (k | v)
+  T* kv = reinterpret_cast<T*>(smem_attn);                // [spb][n_tok][2][hpb*DH]  (k | v of the block's head group)
   const int inner = heads * DH;
   const int seq0 = blockIdx.x * spb;
   const int nseq_here = min(spb, n_seq - seq0);
+  const int h0 = blockIdx.y * hpb, nh = min(hpb, heads - h0), w = hpb * DH;
   // cooperative, 16-byte vectorised copy of the K|V column block of each row
   constexpr int VEC = 16 / sizeof(T);
-  const int vec_per_row = 2 * inner / VEC;
+  const int vec_per_row = 2 * w / VEC;
   const int total_vec = nseq_here * n_tok * vec_per_row;
   for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
-    const int r = i / vec_per_row, c = i - r * vec_per_row;
-    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (size_t(seq0) * n_tok + r) * (3 * inner) + inner + c * VEC);
-    *reinterpret_cast<uint4*>(kv + size_t(r) * 2 * inner + c * VEC) = v;
+    const int r = i / vec_per_row, c = (i - r * vec_per_row) * VEC;
+    const int part = c / w, col = c - part * w;          // 0: k, 1: v
+    if (col >= nh * DH) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + (size_t(seq0) * n_tok + r) * (3 * inner) + size_t(1 + part) * inner + h0 * DH + col);
+    *reinterpret_cast<uint4*>(kv + size_t(r) * 2 * w + c) = v;
   }
   __syncthreads();
-  const int items = nseq_here * heads * n_tok;
+  const int items = nseq_here * nh * n_tok;
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
     const int qi = it % n_tok;
-    const int h = (it / n_tok) % heads;
-    const int sl = it / (n_tok * heads);
+    const int hl = (it / n_tok) % nh, h = h0 + hl;
+    const int sl = it / (n_tok * nh);
     const size_t row = (size_t(seq0 + sl)) * n_tok + qi;
     float q[DH];
     load_frag<T, DH>(qkv + row * (3 * inner) + h * DH, q);
@@ -191,9 +194,9 @@ __global__ void __launch_bounds__(DH == 32 ? 512 : 256) attention_small_kernel(c
     float m = -INFINITY, l = 0.f, acc[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-    const T* kbase = kv + size_t(sl) * n_tok * 2 * inner + h * DH;
+    const T* kbase = kv + size_t(sl) * n_tok * 2 * w + hl * DH;
     for (int j = 0; j < n_tok; ++j) {
-      const T* kp = kbase + size_t(j) * 2 * inner;
+      const T* kp = kbase + size_t(j) * 2 * w;
       float kf[DH];
       load_frag<T, DH>(kp, kf);
       float s = 0.f;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(DH == 32 ? 512 : 256) attention_small_kernel(c
       }
       const float p = exp2f(s - m);
       l += p;
-      load_frag<T, DH>(kp + inner, kf);
+      load_frag<T, DH>(kp + w, kf);
 #pragma unroll
       for (int d = 0; d < DH; ++d) acc[d] = fmaf(p, kf[d], acc[d]);
     }
@@ -251,8 +254,10 @@ int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, 
 template <typename T, int DH>
 static int launch_attention(const void* qkv, void* out, int n_seq, int n_tok, int heads, cudaStream_t st) {
   const int inner = heads * DH;
-  const size_t per_seq = size_t(n_tok) * 2 * inner * sizeof(T);
-  const int threads_per_seq = heads * n_tok;
+  int hpb = heads;                                        // heads staged per block: all of them unless K|V of a sequence exceed 96 KB
+  while (hpb > 1 && size_t(n_tok) * 2 * hpb * DH * sizeof(T) > 96 * 1024) hpb = (hpb + 1) / 2;
+  const size_t per_seq = size_t(n_tok) * 2 * hpb * DH * sizeof(T);
+  const int threads_per_seq = hpb * n_tok;
   constexpr int kMaxThreads = DH == 32 ? 512 : 256;
   int spb = max(1, min(kMaxThreads / threads_per_seq, int((96 * 1024) / per_seq)));
   spb = min(spb, n_seq);
@@ -266,7 +271,8 @@ static int launch_attention(const void* qkv, void* out, int n_seq, int n_tok, in
     cfg = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(DH));
-  kern<<<ceil_div(n_seq, spb), threads, smem, st>>>(static_cast<const T*>(qkv), static_cast<T*>(out), n_seq, n_tok, heads, spb, scale_log2e);
+  kern<<<dim3(ceil_div(n_seq, spb), ceil_div(heads, hpb)), threads, smem, st>>>(static_cast<const T*>(qkv), static_cast<T*>(out), n_seq, n_tok, heads, spb, hpb,
+                                                                               scale_log2e);
   AVF_LAUNCH_CHECK("attention_small_kernel");
   return 0;
 }
