@@ -326,7 +326,12 @@ def run_ours(args):
                     "algorithmic_flop_per_launch": flops_sformer, "traffic_source": roof.get("traffic_source"),
                     "algorithmic_bytes_per_launch": roof.get("algorithmic_bytes"), "share_of_step": ms_sformer / ms_step}
         sample = 64
-        cpu_v, cpu_t, cores = cpu_hot_path_clips_per_s(sample, repeats=3)
+        if world == 1:            # the CPU arm is timed on rank 0 at N=1 only (the other ranks' processes would share the host cores)
+            cpu_v, cpu_t, cores = cpu_hot_path_clips_per_s(sample, repeats=3)
+            cpu_baseline = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
+                            "sample": f"{sample} clips x {T} frames, best of 3, oracle port (torch fp32 CPU) of the same hot path"}
+        else:
+            cpu_baseline = None
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         d2h = out_host.numel() * 4 + dec_host.numel() * 4
         line = {
@@ -339,8 +344,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} clips x {T} frames, best of 3, oracle port (torch fp32 CPU) of the same hot path"},
+            "cpu_baseline": cpu_baseline,
             "tensor_frac_whole_step": value / world * hot_path_flops_per_clip(T) / 1e12 / peaks["bf16_tflops_sustained"],
             "breakdown_ms": {"sformer": ms_sformer, "tformer": ms_tformer, "whole_step": ms_step, "whole_step_eager_launches": ms_eager},
             "launch_mode": "one CUDA-graph replay per step (captured from the library's own kernel launches; gpu_launches counts the kernels inside it)",
