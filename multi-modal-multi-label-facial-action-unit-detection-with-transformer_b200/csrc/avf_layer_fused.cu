@@ -661,7 +661,10 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
 // ---------------------------------------------------------------------------------------------
 // MMA issuer (one thread)
 // ---------------------------------------------------------------------------------------------
+// Executed by ALL 32 lanes of warp 1 with warp-uniform values (so that descriptors and addresses live in uniform registers and
+// the issue loop is a handful of instructions per MMA); only the elected lane issues tcgen05.mma / tcgen05.commit.
 __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint32_t tmem) {
+  const bool leader = elect_one();
   const uint32_t a0 = smem_u32(smem + OFF_A0), a1 = smem_u32(smem + OFF_A1);
   const uint32_t qs = smem_u32(smem + OFF_Q), ks = smem_u32(smem + OFF_K), vs = smem_u32(smem + OFF_V);
   const uint32_t ring = smem_u32(smem + OFF_RING);
@@ -670,7 +673,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
                  id_128 = make_idesc_bf16(128, 128);
   uint32_t it = 0, n_a0 = 0, n_hready[2] = {0, 0};
   Prof pf;
-  pf.start(blockIdx.x == 0);
+  pf.start(blockIdx.x == 0 && leader);
   int ring_phase = PM_QKV;
   auto slot_wait = [&]() -> uint32_t {
     const uint32_t s = it % RING, ph = (it / RING) & 1;
@@ -681,7 +684,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     return ring + s * SLOT_BYTES;
   };
   auto slot_release = [&]() {
-    umma_commit(&bars[B_RING_EMPTY + it % RING]);
+    if (leader) umma_commit(&bars[B_RING_EMPTY + it % RING]);
     ++it;
   };
   auto qkv = [&]() {                          // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T
@@ -689,10 +692,10 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       const uint32_t sb = slot_wait();
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
       slot_release();
     }
-    umma_commit(&bars[B_D1_FULL]);
+    if (leader) umma_commit(&bars[B_D1_FULL]);
   };
   bool last_layer = false;
   auto ff1 = [&](int c) {                     // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
@@ -701,11 +704,11 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       const uint32_t sb = slot_wait();
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (kp | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (kp | k) != 0 ? 1u : 0u);
       slot_release();
     }
-    umma_commit(&bars[B_HACC_FULL + (c & 1)]);
-    if (c == a.n_chunks - 1 && last_layer) umma_commit(&bars[B_A0_FREE]);
+    if (leader) umma_commit(&bars[B_HACC_FULL + (c & 1)]);
+    if (c == a.n_chunks - 1 && last_layer) if (leader) umma_commit(&bars[B_A0_FREE]);
   };
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -723,9 +726,9 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         pf.mark(PM_WAIT_STAGED);
         {                                     // S[128 x kmax] = Q_h K_h^T
           const uint64_t da = desc_sw64(qs), db = desc_sw64(ks);
-          umma_bf16(tmem + TM_S, da, db, id_s, 0u);
-          umma_bf16(tmem + TM_S, da + 2, db + 2, id_s, 1u);
-          umma_commit(&bars[B_S_FULL]);
+          if (leader) umma_bf16(tmem + TM_S, da, db, id_s, 0u);
+          if (leader) umma_bf16(tmem + TM_S, da + 2, db + 2, id_s, 1u);
+          if (leader) umma_commit(&bars[B_S_FULL]);
         }
         pf.mark(PM_S);
         if (h + 1 < HEADS) qkv();
@@ -735,8 +738,8 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         tc_fence_after();
         pf.mark(PM_WAIT_P);
         for (int k = 0; k < kmax / 16; ++k)   // O[128 x 32] = P V_h   (A from TMEM, B MN-major)
-          umma_bf16_ts(tmem + TM_O, tmem + TM_S + uint32_t(k * 8), desc_sw64(vs + (h & 1) * 8192 + k * 1024), id_pv, k != 0 ? 1u : 0u);
-        umma_commit(&bars[B_O_FULL]);
+          if (leader) umma_bf16_ts(tmem + TM_O, tmem + TM_S + uint32_t(k * 8), desc_sw64(vs + (h & 1) * 8192 + k * 1024), id_pv, k != 0 ? 1u : 0u);
+        if (leader) umma_commit(&bars[B_O_FULL]);
         pf.mark(PM_PV);
       }
       mbar_wait(&bars[B_O_DRAINED], (HEADS - 1) & 1);
@@ -748,10 +751,10 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
           const uint32_t sb = slot_wait();
           const uint64_t da = make_desc_sw128_kmajor(a1 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
+          for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
           slot_release();
         }
-      umma_commit(&bars[B_X1_FULL]);
+      if (leader) umma_commit(&bars[B_X1_FULL]);
       pf.mark(PM_OUT);
 
       mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
@@ -772,17 +775,17 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
             const uint32_t sb = slot_wait();
             const uint64_t da = make_desc_sw128_kmajor(a1 + b * 32768 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
+            for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
             slot_release();
           }
         pf.mark(PM_FF2);
         ring_phase = PM_FF1;
         if (c + 2 < a.n_chunks) {
-          umma_commit(&bars[B_HBUF_FREE + b]);
+          if (leader) umma_commit(&bars[B_HBUF_FREE + b]);
           ff1(c + 2);
         }
       }
-      umma_commit(&bars[B_X2_FULL]);
+      if (leader) umma_commit(&bars[B_X2_FULL]);
     }
   }
 }
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
   if (warp == 0) {
     if (lane == 0) producer_main<IO>(a, smem, bars);
   } else if (warp == 1) {
-    if (lane == 0) mma_main(a, smem, bars, tmem);
+    mma_main(a, smem, bars, tmem);
   } else {
     worker_main<IO>(a, smem, bars, tmem);
   }
