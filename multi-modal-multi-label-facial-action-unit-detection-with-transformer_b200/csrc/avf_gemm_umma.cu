@@ -164,8 +164,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Warps 0 and 1 run their loops with all 32 lanes on warp-uniform values (addresses, descriptors and loop state then live in
+  // uniform registers and the issue loops are a few instructions per TMA / MMA); only the elected lane issues.
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int split = tile / mn_tiles, mn = tile - split * mn_tiles;
@@ -175,25 +178,29 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          if constexpr (A_MN) {
+          if (leader) {
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            if constexpr (A_MN) {
 #pragma unroll
-            for (int p = 0; p < BM / 64; ++p) tma_load_2d(st + p * 8192, &tm_a, &full_bar[s], m0 + p * 64, kb * BK);
-          } else {
-            tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
-          }
-          if constexpr (B_MN) {
+              for (int p = 0; p < BM / 64; ++p) tma_load_2d(st + p * 8192, &tm_a, &full_bar[s], m0 + p * 64, kb * BK);
+            } else {
+              tma_load_2d(st, &tm_a, &full_bar[s], kb * BK, m0);
+            }
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int p = 0; p < BN / 64; ++p) tma_load_2d(st + Cfg::A_BYTES + p * 8192, &tm_w, &full_bar[s], n0 + p * 64, kb * BK);
-          } else {
-            tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+              for (int p = 0; p < BN / 64; ++p) tma_load_2d(st + Cfg::A_BYTES + p * 8192, &tm_w, &full_bar[s], n0 + p * 64, kb * BK);
+            } else {
+              tma_load_2d(st + Cfg::A_BYTES, &tm_w, &full_bar[s], kb * BK, n0);
+            }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -215,11 +222,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint64_t db = B_MN ? make_desc(a_addr + Cfg::A_BYTES, 8192, 1024, 2) : make_desc_sw128_kmajor(a_addr + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(tmem_d, da + uint64_t(k * (A_MN ? 128 : 2)), db + uint64_t(k * (B_MN ? 128 : 2)), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            if (leader) umma_bf16(tmem_d, da + uint64_t(k * (A_MN ? 128 : 2)), db + uint64_t(k * (B_MN ? 128 : 2)), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs have read it
+          if (leader) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs have read it
         }
-        umma_commit(&acc_full[buf]);              // accumulator complete
+        if (leader) umma_commit(&acc_full[buf]);  // accumulator complete
       }
     }
   } else if (warp >= 4) {

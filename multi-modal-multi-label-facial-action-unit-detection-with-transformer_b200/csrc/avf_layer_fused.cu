@@ -584,6 +584,9 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
 // ---------------------------------------------------------------------------------------------
 template <int IO>
 __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
+  // (one lane only: this loop polls with try_wait between slots, and a whole-warp version — every lane polling and adopting the
+  //  issuing lane's observation — measured 7x slower; the MMA warp, which blocks instead of polling, does run warp-wide)
+  constexpr bool leader = true;
   uint32_t it = 0;
   // Input frames of the NEXT tile go into A0 as soon as the MMAs of the current tile are done with it (B_A0_FREE, one
   // completion per tile).  Polled between weight slots so that this thread never blocks on it.
@@ -598,8 +601,10 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     }
     const int seqs_here = min(a.spt, a.n_seq - load_tile * a.spt);
     const uint32_t bytes = uint32_t(seqs_here) * a.n_tok * DIM * 2;
-    mbar_expect_tx(&bars[B_X0_FULL], bytes);
-    bulk_load_1d(smem + OFF_A0, static_cast<const __nv_bfloat16*>(a.in) + size_t(load_tile) * a.spt * a.n_tok * DIM, bytes, &bars[B_X0_FULL]);
+    if (leader) {
+      mbar_expect_tx(&bars[B_X0_FULL], bytes);
+      bulk_load_1d(smem + OFF_A0, static_cast<const __nv_bfloat16*>(a.in) + size_t(load_tile) * a.spt * a.n_tok * DIM, bytes, &bars[B_X0_FULL]);
+    }
     load_tile += gridDim.x;
     need_free = true;
   };
@@ -614,7 +619,7 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
         __trap();
       }
     }
-    mbar_expect_tx(&bars[B_RING_FULL + s], bytes);
+    if (leader) mbar_expect_tx(&bars[B_RING_FULL + s], bytes);
     return smem + OFF_RING + s * SLOT_BYTES;
   };
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -624,19 +629,19 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
         for (int kp = 0; kp < 4; ++kp) {
           uint8_t* d = slot(3 * 32 * 128);
           uint64_t* fb = &bars[B_RING_FULL + it % RING];
-          for (int s3 = 0; s3 < 3; ++s3) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
+          for (int s3 = 0; s3 < 3; ++s3) if (leader) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
           ++it;
         }
       for (int kp = 0; kp < 4; ++kp)
         for (int nh = 0; nh < 2; ++nh) {
           uint8_t* d = slot(SLOT_BYTES);
-          tma_load_2d(d, &L.tm_out, &bars[B_RING_FULL + it % RING], kp * 64, nh * 128);
+          if (leader) tma_load_2d(d, &L.tm_out, &bars[B_RING_FULL + it % RING], kp * 64, nh * 128);
           ++it;
         }
       auto ff1 = [&](int c) {
         for (int kp = 0; kp < 4; ++kp) {
           uint8_t* d = slot(SLOT_BYTES);
-          tma_load_2d(d, &L.tm_w1, &bars[B_RING_FULL + it % RING], kp * 64, c * 128);
+          if (leader) tma_load_2d(d, &L.tm_w1, &bars[B_RING_FULL + it % RING], kp * 64, c * 128);
           ++it;
         }
       };
@@ -644,7 +649,7 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
         for (int kp = 0; kp < 2; ++kp)
           for (int nh = 0; nh < 2; ++nh) {
             uint8_t* d = slot(SLOT_BYTES);
-            tma_load_2d(d, &L.tm_w2, &bars[B_RING_FULL + it % RING], c * 128 + kp * 64, nh * 128);
+            if (leader) tma_load_2d(d, &L.tm_w2, &bars[B_RING_FULL + it % RING], c * 128 + kp * 64, nh * 128);
             ++it;
           }
       };
