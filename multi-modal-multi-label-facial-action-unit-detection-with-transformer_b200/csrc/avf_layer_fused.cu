@@ -87,7 +87,7 @@ struct Prof {
 #endif
 // worker phases
 enum { PW_INPUT = 0, PW_VEC, PW_LN1, PW_WAIT_D1, PW_E1, PW_WAIT_O, PW_E3, PW_WAIT_S, PW_E2, PW_WAIT_X1, PW_LN2, PW_WAIT_HACC, PW_GELU, PW_WAIT_X2,
-       PW_OUTPUT, PW_TILES,
+       PW_OUTPUT, PW_TILES, PW_E2_LD, PW_E2_EXP, PW_E2_XCH, PW_E2_ST,
        // MMA thread phases
        PM_WAIT_A0 = 32, PM_QKV, PM_WAIT_STAGED, PM_S, PM_WAIT_P, PM_PV, PM_WAIT_OD7, PM_OUT, PM_WAIT_A0B, PM_FF1, PM_WAIT_H, PM_FF2, PM_RINGWAIT };
 
@@ -134,6 +134,16 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
+               : "memory");
+}
+// zero the TMEM columns [lo, hi) of this warp's lanes (lo, hi multiples of 4; warp-uniform; empty when hi <= lo)
+__device__ __forceinline__ void zero_p_columns(uint32_t taddr, int lo, int hi) {
+  int c = lo;
+  for (; c + 16 <= hi; c += 16) tmem_st16_zero(taddr + c);
+  for (; c + 4 <= hi; c += 4) tmem_st4(taddr + c, 0u, 0u, 0u, 0u);
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -190,6 +200,15 @@ struct Worker {
     bar_sync(1 + q, 32 * NSPLIT);
     return s + row * 4;
   }
+  // exchange of a PAIR of floats between the two threads of a row (one barrier): returns the partner's pair
+  __device__ __forceinline__ float2 exchange_pair(float a, float b) {
+    static_assert(NSPLIT == 2, "pair exchange is written for two threads per row");
+    float* s = reinterpret_cast<float*>(smem + OFF_XCH) + xslot * (128 * 4);
+    xslot ^= 1;
+    *reinterpret_cast<float2*>(s + row * 4 + g * 2) = make_float2(a, b);
+    bar_sync(1 + q, 32 * NSPLIT);
+    return *reinterpret_cast<const float2*>(s + row * 4 + (g ^ 1) * 2);
+  }
   __device__ __forceinline__ float exchange_sum(float mine) {
     const float* v = exchange(mine);
     if constexpr (NSPLIT == 2) return v[0] + v[1];
@@ -204,6 +223,11 @@ struct Worker {
   }
   __device__ __forceinline__ void arrive(int bar) {             // one arrive per warp, after every lane's fences
     fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[bar]);
+  }
+  __device__ __forceinline__ void arrive_tmem_only(int bar) {   // the phase wrote TMEM only (no shared-memory operand for the async proxy)
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[bar]);
@@ -446,7 +470,11 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           for (int c = 0; c < MAXC; ++c)
             if (c < my_nc) tmem_ld8(tl + TM_S + (my_c0 + c) * 8, reinterpret_cast<uint32_t(&)[8]>(s[c]));
           tmem_ld_wait();
-          float mx = -INFINITY;
+          pf.mark(PW_E2_LD);
+          // one exchange per head: every thread exponentiates against the maximum of ITS columns first, the two threads of the
+          // row then swap (max, sum) and rescale by 2^(own max - row max) — the swap also orders every S load of the row
+          // before any P store (P is written over the S columns)
+          float mloc = -INFINITY;
 #pragma unroll
           for (int c = 0; c < MAXC; ++c) {
             if (c < my_nc) {
@@ -455,31 +483,40 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
 #pragma unroll
                 for (int j = 0; j < 8; ++j) s[c][j] = (col0 + j >= lo && col0 + j < hi) ? s[c][j] : -INFINITY;
               }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) mx = fmaxf(mx, s[c][j]);
+              mloc = fmaxf(mloc, fmaxf(fmaxf(fmaxf(s[c][0], s[c][1]), fmaxf(s[c][2], s[c][3])), fmaxf(fmaxf(s[c][4], s[c][5]), fmaxf(s[c][6], s[c][7]))));
             }
           }
-          mx = w.exchange_max(mx);             // also orders every S load of the row before any P store
-          const float nmx = -mx * sm_scale;
-          float sum = 0.f;
+          const float nml = mloc == -INFINITY ? 0.f : -mloc * sm_scale;      // a thread without valid columns contributes zeros
+          float sum_g = 0.f;
 #pragma unroll
           for (int c = 0; c < MAXC; ++c) {
             if (c < my_nc) {
-              float p[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                p[j] = fast_exp2(fmaf(s[c][j], sm_scale, nmx));
-                sum += p[j];
-              }
-              tmem_st4(tl + TM_S + (my_c0 + c) * 4, pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
+              for (int j = 0; j < 8; ++j) s[c][j] = fast_exp2(fmaf(s[c][j], sm_scale, nml));
+              sum_g += ((s[c][0] + s[c][1]) + (s[c][2] + s[c][3])) + ((s[c][4] + s[c][5]) + (s[c][6] + s[c][7]));
             }
           }
-          // P columns the MMA reads (all 128) but this warp's rows never use: zeros (split between the row's threads)
-          for (int c = g; c < 16; c += NSPLIT)
-            if (c < c_lo || c >= c_hi) tmem_st4(tl + TM_S + c * 4, 0u, 0u, 0u, 0u);
-          inv_l = 1.f / w.exchange_sum(sum);
+          pf.mark(PW_E2_EXP);
+          const float2 other = w.exchange_pair(mloc, sum_g);
+          pf.mark(PW_E2_XCH);
+          const float mrow = fmaxf(mloc, other.x);
+          const float f = fast_exp2((mloc - mrow) * sm_scale), fo = fast_exp2((other.x - mrow) * sm_scale);    // 2^(-inf) = 0
+          inv_l = 1.f / fmaf(sum_g, f, other.y * fo);
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < my_nc)
+              tmem_st4(tl + TM_S + (my_c0 + c) * 4, pack_bf16x2(s[c][0] * f, s[c][1] * f), pack_bf16x2(s[c][2] * f, s[c][3] * f),
+                       pack_bf16x2(s[c][4] * f, s[c][5] * f), pack_bf16x2(s[c][6] * f, s[c][7] * f));
+          }
+          // P columns the MMA reads (all 128) but this warp's rows never use: zeros; thread g takes TMEM columns [32g, 32g + 32)
+          {
+            const int z_lo = g * 32, z_hi = z_lo + 32, w_lo = c_lo * 4, w_hi = c_hi * 4;
+            zero_p_columns(tl + TM_S, z_lo, min(z_hi, max(z_lo, w_lo)));
+            zero_p_columns(tl + TM_S, max(z_lo, min(z_hi, w_hi)), z_hi);
+          }
           tmem_st_wait();
-          w.arrive(B_P_READY);
+          pf.mark(PW_E2_ST);
+          w.arrive_tmem_only(B_P_READY);
           pf.mark(PW_E2);
         }
       }

@@ -28,6 +28,8 @@ tw = sum(buf[i] for i in range(15)); tm = sum(buf[32 + i] for i in range(len(M))
 print("worker thread: total %.0f" % (tw / tiles))
 for i, n in enumerate(W):
     print(f"   {n:10s} {buf[i] / tiles:9.0f}  {100 * buf[i] / tw:5.1f}%")
+for i, n in enumerate(["E2_LD", "E2_EXP", "E2_XCH", "E2_ST(rest of E2 = arrive)"]):
+    print(f"   (inside E2) {n:10s} {buf[16 + i] / tiles:9.0f}")
 print("MMA thread: total %.0f" % (tm / tiles))
 for i, n in enumerate(M):
     print(f"   {n:12s} {buf[32 + i] / tiles:9.0f}  {100 * buf[32 + i] / tm:5.1f}%")
