@@ -294,7 +294,7 @@ def run_ours(args):
             return a.elapsed_time(b) / reps
 
         ms_sformer = time_fn(lambda: vm.s_former.sformer(devin["stage3"]))
-        ms_tformer = time_fn(lambda: vm.t_former.tokens(devin["frame"]))
+        ms_tformer = time_fn(lambda: vm.t_former.cls_features(devin["frame"]))
         roof = A.functional.sformer_roofline_probe(devin["stage3"], vm.s_former, time_fn) \
             if hasattr(A.functional, "sformer_roofline_probe") else None
 

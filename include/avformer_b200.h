@@ -135,6 +135,12 @@ size_t avf_sformer_workspace_bytes(const avf_stack_shape* s, int mode);
  * cat(cls, frames) + pos[T+1, dim] */
 int avf_tformer_embed(int io_mode, const void* frames, const float* cls_token, const float* pos, float* x,
                       int32_t n_clips, int32_t n_frames, int32_t dim, void* stream);
+/* Whole TFormer (models/vformer.py:279-290) for inference: embed, `depth` layers, cls rows -> cls_out [n_clips, dim] fp32.  s->n_seq
+ * = clips, s->n_tok = T+1.  Only x[:, 0] leaves the module, so the LAST layer computes keys / values for every row but the attention
+ * output, out-projection, LayerNorm and MLP for the cls row of each clip only (1/(T+1) of that work). */
+size_t avf_tformer_workspace_bytes(const avf_stack_shape* s, int mode);
+int avf_tformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_layer_weights* layers, const void* frames,
+                    const float* cls_token, const float* pos, float* cls_out, void* workspace, size_t workspace_bytes, void* stream);
 /* cls[c,:] = x[c*(T+1), :] */
 int avf_tformer_cls_extract(const float* x, float* cls, int32_t n_clips, int32_t n_tok, int32_t dim, void* stream);
 

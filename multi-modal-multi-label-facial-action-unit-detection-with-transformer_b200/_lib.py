@@ -68,6 +68,9 @@ SIGNATURES = {
     "avf_sformer_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _c_p,
                                        _c_p, _c_p, _sz, _c_p]),
     "avf_tformer_embed": (ctypes.c_int, [ctypes.c_int, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _c_p]),
+    "avf_tformer_workspace_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
+    "avf_tformer_fwd": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _c_p, _c_p, _c_p,
+                                       _c_p, _sz, _c_p]),
     "avf_tformer_cls_extract": (ctypes.c_int, [_c_p, _c_p, _i32, _i32, _i32, _c_p]),
     "avf_au_former_front_fwd": (ctypes.c_int, [ctypes.c_int, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32,
                                                _c_p, _sz, _c_p]),

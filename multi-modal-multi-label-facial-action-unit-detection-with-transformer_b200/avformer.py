@@ -110,8 +110,8 @@ class TwoStreamAuralVisualFormer(nn.Module):
         self.audio_model.au_head.tokens_into(a_feat, a_feat.shape[1], bs, out=fused, ld_out=256)
         # video: conv stages (torch) -> SFormer -> layer4/pool (torch) -> TFormer -> AU_former into columns [128,256)
         frames = vm.s_former(clip[:, -vm.num_channels:].permute(0, 2, 1, 3, 4))
-        tok, n_clips = vm.t_former.tokens(frames)
-        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        cls = vm.t_former.cls_features(frames)
+        self.video_model.au_head.tokens_into(cls, cls.shape[1], cls.shape[0], out=fused[:, 128:], ld_out=256)
         if self.task != "AU":
             return torch.zeros(bs, 21, device=clip.device)
         return self.au_head.logits21_(fused, bs)
@@ -162,11 +162,12 @@ class TwoStreamAuralVisualFormer(nn.Module):
         are fed independently.  Returns (sformer_out, out21 [B,21]) (+ int32 decisions [B,12])."""
         vm = self.video_model.video_model
         s_out = vm.s_former.sformer(stage3)
-        tok, n_clips = vm.t_former.tokens(frame_feat)
-        fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=tok.device)
+        cls = vm.t_former.cls_features(frame_feat)
+        n_clips = cls.shape[0]
+        fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=cls.device)
         a_feat = audio_feat if (audio_feat.dtype == torch.float32 and audio_feat.is_contiguous()) else audio_feat.float().contiguous()
         self.audio_model.au_head.tokens_into(a_feat, a_feat.shape[1], n_clips, out=fused, ld_out=256)
-        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        self.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         res = self.au_head.logits21_(fused, n_clips, want_decisions)
         return (s_out,) + (res if want_decisions else (res,))
 
@@ -207,10 +208,11 @@ class TwoStreamAuralVisualFormer(nn.Module):
                 ev.record(cs)
         vm = self.video_model.video_model
         main.wait_event(st["ev_small"])
-        tok, n_clips = vm.t_former.tokens(st["frame"])
+        cls = vm.t_former.cls_features(st["frame"])
+        n_clips = cls.shape[0]
         fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=dev)
         self.audio_model.au_head.tokens_into(st["audio"], st["audio"].shape[1], n_clips, out=fused, ld_out=256)
-        self.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        self.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         out21, dec = self.au_head.logits21_(fused, n_clips, True)
         if out_host is not None:
             out_host.copy_(out21, non_blocking=True)

@@ -252,6 +252,57 @@ int avf_tformer_embed(int io_mode, const void* frames, const float* cls_token, c
   return tformer_embed(io_mode, frames, cls_token, pos, x, n_clips, n_frames, dim, static_cast<cudaStream_t>(stream));
 }
 
+size_t avf_tformer_workspace_bytes(const avf_stack_shape* s, int mode) {
+  if (s == nullptr || s->n_seq <= 0 || s->n_tok <= 0) return 0;
+  const size_t B = s->n_seq, D = s->dim, I = size_t(s->heads) * s->dim_head, M = s->mlp_dim, e = elt(mode);
+  return align_up(B * s->n_tok * D * 4) + carve_encoder_ws(s, mode, nullptr).total + align_up(B * D * 4) + align_up(B * D * e) + align_up(B * I * e) +
+         align_up(B * M * e);
+}
+
+int avf_tformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_layer_weights* layers, const void* frames,
+                    const float* cls_token, const float* pos, float* cls_out, void* workspace, size_t workspace_bytes, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  if ((e = check_shape(s))) return e;
+  AVF_REQUIRE(layers && frames && cls_token && pos && cls_out && workspace, AVF_EINVAL, "tformer_fwd: null pointer");
+  AVF_REQUIRE(s->n_tok >= 2, AVF_EINVAL, "tformer_fwd: n_tok=%d (cls + at least one frame)", s->n_tok);
+  const size_t need = avf_tformer_workspace_bytes(s, mode);
+  AVF_REQUIRE(workspace_bytes >= need, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = s->n_seq, N = s->n_tok, R = B * N, D = s->dim, I = s->heads * s->dim_head, M = s->mlp_dim;
+  uint8_t* p = static_cast<uint8_t*>(workspace);
+  float* x = reinterpret_cast<float*>(p);   p += align_up(size_t(R) * D * 4);
+  void* enc_ws = p;
+  const EncoderWs w = carve_encoder_ws(s, mode, enc_ws);
+  p += w.total;
+  float* xc = reinterpret_cast<float*>(p);  p += align_up(size_t(B) * D * 4);
+  void* lnc = p;                            p += align_up(size_t(B) * D * elt(mode));
+  void* oc = p;                             p += align_up(size_t(B) * I * elt(mode));
+  void* hc = p;
+  if ((e = tformer_embed(io_mode, frames, cls_token, pos, x, B, N - 1, D, st))) return e;
+  if (s->depth > 1) {
+    avf_stack_shape head = *s;
+    head.depth = s->depth - 1;
+    if ((e = encoder_stack(mode, &head, layers, x, D, nullptr, 0, enc_ws, w.total, st))) return e;
+  }
+  // Last layer (models/vformer.py:288-290 returns x[:, 0] only): keys / values need every row, everything after the softmax only
+  // the cls row of each clip — out-projection, LayerNorm, MLP run on [n_clips, dim] instead of [n_clips * (T+1), dim].
+  const avf_layer_weights& W = layers[s->depth - 1];
+  if ((e = layernorm(mode, x, D, W.ln1_gamma, W.ln1_beta, w.ln, R, D, st))) return e;
+  if ((e = linear(mode, w.ln, D, W.w_qkv, nullptr, nullptr, 0, w.qkv, 3 * I, mode, R, 3 * I, D, 0, st))) return e;
+  if (mode == AVF_BF16) {
+    if ((e = attention_mma_bf16(w.qkv, oc, B, N, s->heads, s->dim_head, st, 1))) return e;
+  } else {
+    if ((e = attention_small(mode, w.qkv, w.attn, B, N, s->heads, s->dim_head, st))) return e;
+    AVF_CUDA(cudaMemcpy2DAsync(oc, size_t(I) * 4, w.attn, size_t(N) * I * 4, size_t(I) * 4, B, cudaMemcpyDeviceToDevice, st));
+  }
+  if ((e = rows_gather(x, size_t(N) * D, xc, B, D, st))) return e;
+  if ((e = linear(mode, oc, I, W.w_out, W.b_out, xc, D, xc, D, AVF_FP32, B, D, I, AVF_EPI_BIAS | AVF_EPI_RESIDUAL, st))) return e;
+  if ((e = layernorm(mode, xc, D, W.ln2_gamma, W.ln2_beta, lnc, B, D, st))) return e;
+  if ((e = linear(mode, lnc, D, W.w_ff1, W.b_ff1, nullptr, 0, hc, M, mode, B, M, D, AVF_EPI_BIAS | AVF_EPI_GELU, st))) return e;
+  return linear(mode, hc, M, W.w_ff2, W.b_ff2, xc, D, cls_out, D, AVF_FP32, B, D, M, AVF_EPI_BIAS | AVF_EPI_RESIDUAL, st);
+}
+
 int avf_tformer_cls_extract(const float* x, float* cls, int32_t n_clips, int32_t n_tok, int32_t dim, void* stream) {
   int e = require_device();
   if (e) return e;

@@ -26,7 +26,9 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 
 template <int DH, int NP>    // NP = tokens padded to a multiple of 16 (16 / 32 / 48 / 64)
 __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                            int n_problems, int n_tok, int heads, float scale_log2e) {
+                                                            int n_problems, int n_tok, int heads, float scale_log2e, int q_rows) {
+  // q_rows: only the first q_rows query rows of every sequence are computed and written (compactly: out [n_seq * q_rows, inner]);
+  // q_rows = n_tok is plain self-attention, q_rows = 1 is the TFormer's last layer, of which only the cls row is consumed.
   constexpr int PITCH = DH + 8;                       // elements; (DH*2+16) bytes keeps 8 consecutive rows on distinct banks
   constexpr int WARPS = DH == 32 ? 4 : 2;             // keeps the static slab under 48 KB
   __shared__ __align__(16) __nv_bfloat16 smem[WARPS][2][NP][PITCH];
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(cons
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
   for (int mt = 0; mt < NP / 16; ++mt) {
-    if (mt * 16 >= n_tok) break;
+    if (mt * 16 >= q_rows) break;
     const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
     // Q fragments (A operand, row-major 16x16 per k-step) straight from global
     uint32_t qf[DH / 16][4];
@@ -131,23 +133,23 @@ __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(cons
       }
     }
     const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
-    __nv_bfloat16* olo = out + (row0 + r_lo) * inner + head * DH + 2 * t;
-    __nv_bfloat16* ohi = out + (row0 + r_hi) * inner + head * DH + 2 * t;
+    __nv_bfloat16* olo = out + (size_t(seq) * q_rows + r_lo) * inner + head * DH + 2 * t;
+    __nv_bfloat16* ohi = out + (size_t(seq) * q_rows + r_hi) * inner + head * DH + 2 * t;
 #pragma unroll
     for (int nt = 0; nt < DH / 8; ++nt) {
-      if (r_lo < n_tok) *reinterpret_cast<uint32_t*>(olo + nt * 8) = pack_bf16x2(o[nt][0] * i_lo, o[nt][1] * i_lo);
-      if (r_hi < n_tok) *reinterpret_cast<uint32_t*>(ohi + nt * 8) = pack_bf16x2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+      if (r_lo < q_rows) *reinterpret_cast<uint32_t*>(olo + nt * 8) = pack_bf16x2(o[nt][0] * i_lo, o[nt][1] * i_lo);
+      if (r_hi < q_rows) *reinterpret_cast<uint32_t*>(ohi + nt * 8) = pack_bf16x2(o[nt][2] * i_hi, o[nt][3] * i_hi);
     }
   }
 }
 
 template <int DH, int NP>
-int launch(const void* qkv, void* out, int n_seq, int n_tok, int heads, cudaStream_t st) {
+int launch(const void* qkv, void* out, int n_seq, int n_tok, int heads, int q_rows, cudaStream_t st) {
   const int n_problems = n_seq * heads;
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(DH));
   constexpr int kWarps = DH == 32 ? 4 : 2;
   attention_mma_kernel<DH, NP><<<ceil_div(n_problems, kWarps), kWarps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                                                                      n_problems, n_tok, heads, scale_log2e);
+                                                                      n_problems, n_tok, heads, scale_log2e, q_rows);
   AVF_LAUNCH_CHECK("attention_mma_kernel");
   return 0;
 }
@@ -379,10 +381,11 @@ int launch_bwd(const void* qkv, const void* dout, void* dqkv, int n_seq, int n_t
 
 }  // namespace
 
-int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st) {
+int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st, int q_rows) {
   AVF_REQUIRE(n_tok >= 1 && n_tok <= 64, AVF_EUNSUPPORTED, "attention: n_tok=%d (1..64)", n_tok);
+  if (q_rows <= 0 || q_rows > n_tok) q_rows = n_tok;
   const int np = (n_tok + 15) / 16 * 16;
-#define AVF_ATT(D, P) if (dim_head == D && np == P) return launch<D, P>(qkv, out, n_seq, n_tok, heads, st);
+#define AVF_ATT(D, P) if (dim_head == D && np == P) return launch<D, P>(qkv, out, n_seq, n_tok, heads, q_rows, st);
   AVF_ATT(32, 16) AVF_ATT(32, 32) AVF_ATT(32, 48) AVF_ATT(32, 64)
   AVF_ATT(64, 16) AVF_ATT(64, 32) AVF_ATT(64, 48) AVF_ATT(64, 64)
 #undef AVF_ATT

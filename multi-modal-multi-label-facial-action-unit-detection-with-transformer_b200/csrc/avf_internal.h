@@ -56,7 +56,7 @@ int adam_step(float* p, const float* g, float* m, float* v, void* shadow, size_t
               int decoupled, float grad_scale, cudaStream_t st);
 
 // avf_attention_mma.cu
-int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
+int attention_mma_bf16(const void* qkv, void* out, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st, int q_rows = 0);
 int attention_bwd_mma_bf16(const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, int dim_head, cudaStream_t st);
 
 // avf_layer_fused.cu: whole encoder stack in one persistent tcgen05 kernel (dim 256, 8 heads x 32)

@@ -204,6 +204,17 @@ def tformer_embed(frames: torch.Tensor, cls_token: torch.Tensor, pos: torch.Tens
     return x
 
 
+def tformer_fwd(frames: torch.Tensor, cls_token: torch.Tensor, pos: torch.Tensor, packed: PackedStack, shape: StackShape) -> torch.Tensor:
+    """Inference TFormer in one call: frames [n_clips*T, dim] -> cls features [n_clips, dim] fp32 (last layer on the cls rows only)."""
+    frames = _cuda(frames, "frames").contiguous()
+    cls = torch.empty((shape.n_seq, shape.dim), dtype=torch.float32, device=frames.device)
+    L = _lib.lib()
+    ws = workspace(L.avf_tformer_workspace_bytes(ctypes.byref(shape), packed.mode), frames.device)
+    check(L.avf_tformer_fwd(packed.mode, _io_mode(frames), ctypes.byref(shape), packed.array, _ptr(frames), _ptr(_f32c(cls_token)), _ptr(_f32c(pos)),
+                            _ptr(cls), _ptr(ws), ws.numel(), _stream()), "tformer_fwd")
+    return cls
+
+
 def tformer_cls_extract(x: torch.Tensor, n_clips: int, n_tok: int) -> torch.Tensor:
     dim = x.shape[-1]
     cls = torch.empty((n_clips, dim), dtype=torch.float32, device=x.device)

@@ -55,8 +55,8 @@ class GraphedHotPath:
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
             m.audio_model.au_head.tokens_into(self.audio, self.audio.shape[1], n_clips, out=fused, ld_out=256)
-        tok, _ = vm.t_former.tokens(self.frame)
-        m.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        cls = vm.t_former.cls_features(self.frame)
+        m.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         cur.wait_stream(self.side)
         out21, dec = m.au_head.logits21_(fused, n_clips, True)
         s_out = vm.s_former.sformer(self.stage3)

@@ -99,8 +99,8 @@ class InferenceEngine:
         s3 = vm.s_former.sformer(s3.contiguous())                      # NCHW-contiguous map in, same out (models/vformer.py:245-259)
         f = self.video.to_stage(s3.to(self.dtype).contiguous(memory_format=torch.channels_last), 4, 4)
         frame_feat = f.float().mean(dim=(2, 3))                         # AdaptiveAvgPool2d((1,1)) + flatten
-        tok, n_clips = vm.t_former.tokens(frame_feat)
-        m.video_model.au_head.tokens_into(tok, tok.shape[1] * (vm.t_former.num_patches + 1), n_clips, out=fused[:, 128:], ld_out=256)
+        cls = vm.t_former.cls_features(frame_feat)
+        m.video_model.au_head.tokens_into(cls, cls.shape[1], cls.shape[0], out=fused[:, 128:], ld_out=256)
         if m.task != "AU":
             return torch.zeros(bs, 21, device=clip.device)
         return m.au_head.logits21_(fused, bs)

@@ -131,11 +131,24 @@ class TFormer(nn.Module):
         self.spatial_transformer.forward_(tok, n_clips, self.num_patches + 1)
         return tok, n_clips
 
+    def cls_features(self, x):
+        """Inference: cls features [n_clips, dim] fp32 in one library call; the last layer runs its post-softmax part on the cls rows
+        only (the other rows never leave the module, models/vformer.py:290)."""
+        AF._cuda(x, "x")
+        if x.numel() % (self.num_patches * self.dim) != 0:
+            raise ValueError(f"TFormer(num_patches={self.num_patches}): input of {tuple(x.shape)} is not a whole number of clips")
+        n_clips = x.numel() // (self.num_patches * self.dim)
+        st = self.spatial_transformer
+        if st.dropout_state()[0] > 0.0:                 # train() with dropout: the tape-keeping kernels apply it
+            tok, _ = self.tokens(x)
+            return AF.tformer_cls_extract(tok, n_clips, self.num_patches + 1)
+        return AF.tformer_fwd(x.detach(), self.cls_token.view(-1), self.pos_embedding[0], st.packed(), st.shape(n_clips, self.num_patches + 1))
+
     def forward(self, x):
-        tok, n_clips = self.tokens(x)
-        if tok.requires_grad:
+        if needs_grad(self, x):
+            tok, n_clips = self.tokens(x)
             return tok.view(n_clips, self.num_patches + 1, self.dim)[:, 0]          # cls rows (a view: data movement only)
-        return AF.tformer_cls_extract(tok, n_clips, self.num_patches + 1)
+        return self.cls_features(x)
 
 
 class VideoModel(nn.Module):
