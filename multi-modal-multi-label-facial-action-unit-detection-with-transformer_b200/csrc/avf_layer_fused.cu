@@ -349,43 +349,40 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
     float mean, rstd;
     {
       Worker::Stats st{0.f, 0.f, 0.f};
-      const float* pp = a.pos != nullptr ? a.pos + t_in_seq * DIM + g * CW : nullptr;
-      float4 p4[8];
-      if (pp != nullptr && valid) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp) + j);
-      }
+      // Branch-free: padding rows (and sequences beyond the end of the batch) read a valid location and are multiplied by zero,
+      // so the 32-value register block is never merged across a divergent branch (which used to put it on the stack).
+      const float vmul = valid ? 1.f : 0.f;
+      const int t_safe = valid ? t_in_seq : 0, seq_safe = valid ? seq_in_tile : 0;
+      const float* pp = a.pos != nullptr ? a.pos + t_safe * DIM + g * CW : nullptr;
       if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
-      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(seq_in_tile * DIM + g * CW) * n_tok + t_in_seq;
-      const float* src32 = static_cast<const float*>(a.in) + grow * a.ld_in + g * CW;
+      const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(seq_safe * DIM + g * CW) * n_tok + t_safe;
+      const float* src32 = static_cast<const float*>(a.in) + ((size_t(tile) * spt + seq_safe) * n_tok + t_safe) * a.ld_in + g * CW;
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
+        float4 p4[8];
+        if (pp != nullptr) {                          // requested first: the L2 round trip overlaps the 32 shared-memory reads below
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp + c0) + j);
+        }
         float x[32];
-        if (valid) {
-          if constexpr (IO == IO_NCHW_BF16) {
+        if constexpr (IO == IO_NCHW_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __bfloat162float(src16[(c0 + j) * n_tok]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 x4 = *reinterpret_cast<const float4*>(src32 + c0 + j);
-              x[j] = x4.x; x[j + 1] = x4.y; x[j + 2] = x4.z; x[j + 3] = x4.w;
-            }
-          }
-          if (pp != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
-            }
-            if (c0 + 32 < CW) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp + c0 + 32) + j);
-            }
-          }
+          for (int j = 0; j < 32; ++j) x[j] = __bfloat162float(src16[(c0 + j) * n_tok]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = 0.f;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(src32 + c0 + j);
+            x[j] = x4.x; x[j + 1] = x4.y; x[j + 2] = x4.z; x[j + 3] = x4.w;
+          }
         }
+        if (pp != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] *= vmul;
         st.add(x, c0 == 0);
         tmem_st32(tl + TM_X + g * CW + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
       }
