@@ -171,7 +171,7 @@ class TwoStreamAuralVisualFormer(nn.Module):
         res = self.au_head.logits21_(fused, n_clips, want_decisions)
         return (s_out,) + (res if want_decisions else (res,))
 
-    def hot_path_from_host(self, stage3_host, frame_host, audio_host, out_host=None, dec_host=None, chunks: int = 4):
+    def hot_path_from_host(self, stage3_host, frame_host, audio_host, out_host=None, dec_host=None, chunks: int = 16):
         """hot_path() for inputs that still sit in (pinned) HOST memory: the public end-to-end entry bench.py's ``e2e`` times.
 
         The stage-3 maps are 95 % of the bytes.  They are copied in ``chunks`` pieces on a dedicated copy stream while the
