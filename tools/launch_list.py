@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Group an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel and print the markdown table kept under profiles/.
 
-    python tools/launch_list.py gpurun_out/launches.csv [skip_first_n] > profiles/rNN_launches_<what>.md
+    python tools/launch_list.py gpurun_out/launches.csv [skip_first_n [count]] > profiles/rNN_launches_<what>.md
 """
 import csv
 import sys
@@ -11,6 +11,7 @@ from collections import OrderedDict
 def main():
     path = sys.argv[1]
     skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    limit = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 60
     lines = [l for l in open(path, errors="replace") if l.startswith('"')]
     rows = list(csv.reader(lines))
     hdr = rows[0]
@@ -21,7 +22,7 @@ def main():
         if len(r) <= col["Metric Value"] or r[col["Metric Name"]] != "gpu__time_duration.sum":
             continue
         n += 1
-        if n <= skip:
+        if n <= skip or n > skip + limit:
             continue
         unit = r[col["Metric Unit"]]
         v = float(r[col["Metric Value"]].replace(",", ""))
