@@ -85,6 +85,15 @@ def to_f32(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def fresh_bf16_image(param: torch.Tensor) -> Optional[torch.Tensor]:
+    """The bf16 copy of ``param`` that optim.FusedAdam's update kernel wrote next to the fp32 master (no cast kernel needed), or
+    None when there is none or the parameter changed since (version counter)."""
+    img = getattr(param, "_avf_bf16", None)
+    if img is not None and img[1] == param._version and img[0].device == param.device:
+        return img[0]
+    return None
+
+
 class PackedStack:
     """Device-side weight table of one encoder stack: an array of avf_layer_weights plus the tensors
     that keep the pointers alive.  ``sources`` are the live nn.Parameters; ``stale()`` compares their
@@ -103,7 +112,9 @@ class PackedStack:
                 self.sources.append(src)
                 t = _f32c(_cuda(src, name))
                 if name in mats and mode == AVF_BF16:
-                    t = to_bf16(t)
+                    t = fresh_bf16_image(src)
+                    if t is None:
+                        t = to_bf16(_f32c(src))
                 self.keep.append(t)
                 setattr(self.array[i], name, t.data_ptr())
         self.versions = [(s.data_ptr(), s._version) for s in self.sources]

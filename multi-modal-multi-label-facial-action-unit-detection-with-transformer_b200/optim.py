@@ -38,7 +38,7 @@ class FusedAdam(torch.optim.Optimizer):
             if p.dtype != torch.float32 or not p.is_cuda:
                 raise TypeError("FusedAdam: parameters must be float32 CUDA tensors (the B200 path has no CPU fallback)")
             offs.append(n)
-            n += (p.numel() + 3) // 4 * 4            # keep every parameter 16-byte aligned inside the bucket
+            n += (p.numel() + 7) // 8 * 8            # 32-byte aligned in the fp32 bucket, 16-byte (TMA) aligned in the bf16 shadow
         flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         with torch.no_grad():
@@ -47,7 +47,8 @@ class FusedAdam(torch.optim.Optimizer):
                 flat_g[o:o + p.numel()].copy_(p.grad.detach().reshape(-1))
                 p.data = flat_p[o:o + p.numel()].view(p.shape)
                 p.grad = flat_g[o:o + p.numel()].view(p.shape)
-        return dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), step=0)
+        shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)       # bf16 copy of the bucket, refreshed by the update kernel
+        return dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         """Bucketed parameters keep their flat gradient views (zeroed with one memset); others follow torch's semantics."""
@@ -95,6 +96,11 @@ class FusedAdam(torch.optim.Optimizer):
                 dist.all_reduce(b["g"], op=dist.ReduceOp.SUM, group=self.process_group)
             b["step"] += 1
             AF.adam_step_(b["p"], b["g"], b["m"], b["v"], b["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                          group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world)
+                          group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world, shadow=b["shadow"])
+            # GEMM operand copies for free: weight matrices point at their bf16 image in the shadow bucket, valid for exactly this
+            # parameter version (load_state_dict / manual edits bump the version and fall back to the cast kernel)
+            for p, o in zip(b["params"], b["offs"]):
+                if p.dim() >= 2:
+                    p._avf_bf16 = (b["shadow"][o:o + p.numel()].view(p.shape), p._version)
         AF.bump_weights_epoch()
         return loss
