@@ -85,6 +85,10 @@ int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05
  * kernel-per-operation path instead (used by the A/B parity tests); returns the previous setting. */
 int         avf_set_fused_enabled(int enabled);
 int         avf_encoder_fused_supported(const avf_stack_shape* s, int mode);
+/* Upper bound on the grid of the persistent kernels (fused encoder, tcgen05 GEMM) launched AFTER the call; 0 = all SMs.
+ * Returns the previous value.  Lets a caller run two kernel chains side by side on disjoint SM sets (each persistent CTA
+ * owns a whole SM): e.g. cap 116 around the SFormer launch, cap 32 around the TFormer / head chain on another stream. */
+int         avf_set_sm_cap(int cap);
 /* Developer aid: 64 per-phase cycle counters of the fused kernel when the library is built with -DAVF_FUSED_PROF
  * (tools/fused_phases.py); AVF_EUNSUPPORTED otherwise. */
 int         avf_debug_fused_prof(uint64_t* out64, int reset);

@@ -16,6 +16,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libavformer_b200.so")
+# Developer A/B runs: AVF_LIB_OVERRIDE=<path of an alternative build of the same sources> is loaded as is (never built here).
+_OVERRIDE = os.environ.get("AVF_LIB_OVERRIDE", "")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -91,6 +93,7 @@ SIGNATURES = {
     "avf_encoder_stack_bwd": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(StackShape), ctypes.POINTER(LayerWeights), _c_p, _sz, _c_p, _i32,
                                              ctypes.POINTER(LayerGrads), ctypes.c_int, _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
     "avf_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p]),
+    "avf_set_sm_cap": (ctypes.c_int, [ctypes.c_int]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
     "avf_layernorm_bwd_workspace_bytes": (_sz, [_i32, _i32]),
@@ -123,21 +126,24 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libavformer_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, out: str = "") -> str:
+    """Compile csrc/*.cu into libavformer_b200.so for sm_100a (nvcc cross-compiles without a GPU).  `out` = alternative
+    output path for developer variants (with AVF_NVCC_EXTRA), loaded through AVF_LIB_OVERRIDE."""
+    if out:
+        force = True
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("avformer_b200: nvcc not found and libavformer_b200.so is missing/stale; cannot build the CUDA path")
     extra = os.environ.get("AVF_NVCC_EXTRA", "").split()          # e.g. -DAVF_FUSED_PROF -DAVF_FUSED_NSPLIT=4 (developer builds)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("avformer_b200: nvcc failed\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 def lib() -> ctypes.CDLL:
@@ -147,12 +153,15 @@ def lib() -> ctypes.CDLL:
         return _lib
     with _lock:
         if _lib is None:
-            try:
-                build()
-            except RuntimeError:
-                if not os.path.exists(LIB_PATH):
-                    raise
-            handle = ctypes.CDLL(LIB_PATH)
+            if _OVERRIDE:
+                handle = ctypes.CDLL(_OVERRIDE)
+            else:
+                try:
+                    build()
+                except RuntimeError:
+                    if not os.path.exists(LIB_PATH):
+                        raise
+                handle = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(handle, name)       # AttributeError here = header/library mismatch: fail loudly
                 fn.restype, fn.argtypes = res, args

@@ -12,6 +12,8 @@ namespace avf {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_sm_cap{0};     // avf_set_sm_cap
+int sm_cap() { return g_sm_cap.load(); }
 static std::atomic<int> g_fused{1};      // avf_set_fused_enabled: 0 forces the kernel-per-op path (A/B tests)
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -110,7 +112,7 @@ static int encoder_stack(int mode, const avf_stack_shape* s, const avf_layer_wei
   AVF_REQUIRE(mode == AVF_BF16 || mode == AVF_FP32, AVF_EINVAL, "mode=%d", mode);
   AVF_REQUIRE(L != nullptr && x != nullptr && ws != nullptr, AVF_EINVAL, "null pointer argument");
   if (mode == AVF_BF16 && g_fused.load() && tcgen05_ok() && encoder_fused_supported(s) && ld_x % 4 == 0 && (out == nullptr || ld_out % 4 == 0))
-    return encoder_fused(1, s, L, x, ld_x, out ? out : x, out ? ld_out : ld_x, nullptr, st);     // whole stack, one persistent kernel
+    return encoder_fused(1, s, L, x, ld_x, out ? out : x, out ? ld_out : ld_x, nullptr, nullptr, st);     // whole stack, one persistent kernel
   const EncoderWs w = carve_encoder_ws(s, mode, ws);
   AVF_REQUIRE(ws_bytes >= w.total, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, w.total);
   const int R = s->n_seq * s->n_tok, D = s->dim, I = s->heads * s->dim_head, M = s->mlp_dim;
@@ -148,6 +150,8 @@ int avf_set_fused_enabled(int enabled) {
   const int old = g_fused.exchange(enabled ? 1 : 0);
   return old;
 }
+
+int avf_set_sm_cap(int cap) { return g_sm_cap.exchange(cap > 0 ? cap : 0); }
 
 int avf_encoder_fused_supported(const avf_stack_shape* s, int mode) {
   return (s != nullptr && mode == AVF_BF16 && s->n_seq > 0 && encoder_fused_supported(s)) ? 1 : 0;
@@ -223,7 +227,7 @@ int avf_sformer_tokens_unpack(int io_mode, const float* x, void* fmap, int32_t n
 
 size_t avf_sformer_workspace_bytes(const avf_stack_shape* s, int mode) {
   if (s == nullptr || s->n_seq <= 0 || s->n_tok <= 0) return 0;
-  return align_up(size_t(s->n_seq) * s->n_tok * s->dim * 4) + carve_encoder_ws(s, mode, nullptr).total;
+  return align_up(size_t(s->n_seq) * s->n_tok * s->dim * 4) + carve_encoder_ws(s, mode, nullptr).total + align_up(encoder_fused_scratch_bytes());
 }
 
 int avf_sformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_layer_weights* layers, const float* pos,
@@ -236,7 +240,7 @@ int avf_sformer_fwd(int mode, int io_mode, const avf_stack_shape* s, const avf_l
   AVF_REQUIRE(workspace_bytes >= need, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == AVF_BF16 && io_mode == AVF_BF16 && g_fused.load() && tcgen05_ok() && encoder_fused_supported(s))
-    return encoder_fused(0, s, layers, fmap_in, 0, fmap_out, 0, pos, st);       // frames in, frames out: nothing else touches HBM
+    return encoder_fused(0, s, layers, fmap_in, 0, fmap_out, 0, pos, workspace, st);   // frames in, frames out: nothing else touches HBM
   float* x = static_cast<float*>(workspace);
   const size_t xbytes = align_up(size_t(s->n_seq) * s->n_tok * s->dim * 4);
   if ((e = sformer_pack(io_mode, fmap_in, pos, x, s->n_seq, s->dim, s->n_tok, st))) return e;

@@ -17,6 +17,7 @@ namespace avf {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch();   // bumps the counter avf_launch_count() reports
+int sm_cap();          // avf_set_sm_cap: upper bound on the grid of the persistent kernels (0 = all SMs)
 
 #define AVF_REQUIRE(cond, code, ...)            \
   do {                                          \

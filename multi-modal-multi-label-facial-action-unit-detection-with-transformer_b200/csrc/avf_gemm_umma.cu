@@ -313,8 +313,9 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-// 2-D bf16 row-major [rows, cols] (row stride ld elements), box = [box_rows x 64 cols], 128B swizzle.
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2-D bf16 row-major [rows, cols] (row stride ld elements), box = [box_rows x box_cols]: 64 cols with the 128B swizzle
+// (default) or 32 cols with the 64B swizzle.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   AVF_REQUIRE(fn != nullptr, AVF_ENODEVICE, "cuTensorMapEncodeTiled is not available from the driver");
   AVF_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, AVF_EINVAL,
@@ -322,10 +323,12 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
               (unsigned long long)ld);
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  AVF_REQUIRE(box_cols == 64 || box_cols == 32, AVF_EINVAL, "tensor map box must be 64 or 32 columns wide");
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AVF_REQUIRE(r == CUDA_SUCCESS, AVF_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return 0;
@@ -358,7 +361,8 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
     configured = true;
   }
   const int n_tiles = (n / BN) * ceil_div(m, BM) * splits;
-  kern<<<min(n_tiles, sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
+  const int cap = sm_cap();
+  kern<<<min(n_tiles, cap > 0 ? min(cap, sm_count()) : sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
                                                                    static_cast<__nv_bfloat16*>(const_cast<void*>(aux)), ld_aux, splits, split_stride, drop);
   AVF_LAUNCH_CHECK("gemm_umma_kernel");
   return 0;

@@ -10,11 +10,15 @@
 //   * attention is per head on the tensor cores: [Q|K|V]_h = LN(x) Wqkv_h^T (N=96), S = Q K^T over the whole tile
 //     (block-diagonal: a row only uses the columns of its own sequence), softmax in registers, P written back as
 //     bf16 INTO the S columns of TMEM and used as the A operand of O = P V (V is an MN-major B operand);
-//   * weights are streamed from L2 by TMA through a 3-slot ring, activations enter / leave as whole NCHW frames
+//   * the out-projection runs PER HEAD (x += O_h Wout[:, 32h:32h+32]^T, N = 256, K = 32) as soon as O_h is normalised, so
+//     there is no attention-output buffer: during the attention phase the 64 KB of A1 hold the O_h staging (2 x 8 KB) and a
+//     second weight ring of 4 x 12 KB = one whole head of [Wq_h; Wk_h; Wv_h], so QKV(h+1) never waits for L2;
+//   * the other weights are streamed from L2 by TMA through a 3-slot ring, activations enter / leave as whole NCHW frames
 //     by bulk copies (SFormer, models/vformer.py:245-259) or as fp32 rows.
 //
-// Warp roles: 0 = TMA producer (weights; also the next tile's input frames), 1 = TMEM allocator + MMA issuer (one thread),
-// 2..17 = row workers (warp w owns TMEM lanes 32*(w%4)..+31; four warps share a lane quarter and split the columns).
+// Warp roles: 0 = TMA producer (out-proj / MLP weights; also the next tile's input frames), 1 = TMEM allocator + MMA issuer
+// (one thread), 2 = TMA producer of the QKV ring, 3.. = row workers (warp w owns TMEM lanes 32*(w%4)..+31; the NSPLIT warps
+// of a lane quarter split the columns).
 #include <cuda.h>
 
 #include "avf_common.cuh"
@@ -22,7 +26,7 @@
 
 namespace avf {
 
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = 64);
 
 namespace {
 
@@ -33,23 +37,28 @@ constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
 #endif
 constexpr int NSPLIT = AVF_FUSED_NSPLIT;   // threads per token row (each owns DIM / NSPLIT columns of the residual stream)
 static_assert(NSPLIT == 2 || NSPLIT == 4, "NSPLIT");
-constexpr int WORKER_T0 = 64;              // first worker thread
+constexpr int WORKER_T0 = 96;              // first worker thread
 constexpr int NUM_WORKERS = 128 * NSPLIT;
 constexpr int NUM_THREADS = WORKER_T0 + NUM_WORKERS;
-constexpr int RING = 3, SLOT_BYTES = 16384;
+constexpr int RING = 5, SLOT_BYTES = 16384;     // main weight ring: slot s at OFF_Q + s * 16 KB; slots 0-1 alias the Q/K/V staging (MLP phase only)
+constexpr int RING_LO = 2;                      // first slot that is free in every phase
+constexpr int QRING = 4, QSLOT_BYTES = 12288;   // QKV ring: one slot = one 64-wide K panel of [Wq_h; Wk_h; Wv_h] (3 x 32 rows x 128 B)
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int OFF_A0 = 0;                          // 64 KB  LN output [128 x 256] bf16, 4 K-panels; also the NCHW input staging
-constexpr int OFF_A1 = 65536;                      // 64 KB  attention output / 2 x GELU(hidden chunk) / NCHW output staging
+constexpr int OFF_A1 = 65536;                      // 64 KB  attention phase: O_h staging + QKV ring; MLP: 2 x GELU(hidden chunk); NCHW output staging
+constexpr int OFF_OST = OFF_A1;                    //   2 x 8 KB  O_h / l  [128 x 32] K-major SW64, double buffered
+constexpr int OFF_QRING = OFF_A1 + 16384;          //   4 x 12 KB QKV weight ring
 constexpr int OFF_Q = 131072;                      // 8 KB   Q_h [128 x 32] K-major SW64
 constexpr int OFF_K = OFF_Q + 8192;                // 8 KB   K_h
 constexpr int OFF_V = OFF_K + 8192;                // 2x8 KB V_h [128 tok x 32] MN-major SW64, double buffered
-constexpr int OFF_RING = OFF_V + 16384;            // 3 x 16 KB weight ring
-constexpr int OFF_XCH = OFF_RING + RING * SLOT_BYTES;   // row exchange [2][128][4] floats
+constexpr int OFF_RING = OFF_V + 16384;            // 3 x 16 KB weight ring (slots 2-4; slots 0-1 = the 32 KB of Q/K/V staging above)
+static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguous from OFF_Q");
+constexpr int OFF_XCH = OFF_RING + (RING - RING_LO) * SLOT_BYTES;   // row exchange [2][128][4] floats
 constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors (LN affine, biases), fp32
 constexpr int V_LN1G = 0, V_LN1B = 256, V_BOUT = 512, V_LN2G = 768, V_LN2B = 1024, V_BFF2 = 1280, V_BFF1 = 1536;
 constexpr int OFF_BAR = OFF_VEC + (V_BFF1 + MAX_MLP) * 4;
-constexpr int SMEM_USED = OFF_BAR + 256;
+constexpr int SMEM_USED = OFF_BAR + 512;
 constexpr int SMEM_ALLOC = SMEM_USED + 1024;       // slack for the 1024-byte alignment of the base
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 
@@ -58,31 +67,44 @@ constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, T
 
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
-  B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_HBUF_FREE, B_HBUF_FREE1, B_X2_FULL, NUM_BARS
+  B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_HBUF_FREE, B_HBUF_FREE1, B_X2_FULL,
+  B_QR_FULL, B_QR_EMPTY = B_QR_FULL + QRING, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, NUM_BARS
 };
-static_assert(NUM_BARS * 8 + 8 <= 256, "barrier block");
+static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
 
 enum { IO_NCHW_BF16 = 0, IO_ROWS_F32 = 1 };
+constexpr int POS_LD = 64;   // row stride of the channel-major positional table
 
 // Optional phase timing (-DAVF_FUSED_PROF): CTA 0's MMA thread and first worker thread accumulate clock64() deltas per phase.
 #ifdef AVF_FUSED_PROF
 __device__ unsigned long long g_prof[64];
-struct Prof {
+struct Prof {      // per-thread accumulators (local memory, L1-resident: a mark costs tens of cycles), flushed to g_prof once at the end
   long long t0;
   bool on;
-  __device__ __forceinline__ void start(bool enable) { on = enable; t0 = clock64(); }
+  unsigned acc[64];
+  __device__ __forceinline__ void start(bool enable) {
+    on = enable;
+    for (int i = 0; i < 64; ++i) acc[i] = 0;
+    t0 = clock64();
+  }
   __device__ __forceinline__ void mark(int idx) {
     if (on) {
       const long long t1 = clock64();
-      g_prof[idx] += (unsigned long long)(t1 - t0);
+      acc[idx] += unsigned(t1 - t0);
       t0 = t1;
     }
+  }
+  __device__ __forceinline__ void count(int idx) { if (on) acc[idx] += 1; }
+  __device__ __forceinline__ void flush(int lo, int hi) {
+    if (on) for (int i = lo; i < hi; ++i) g_prof[i] += acc[i];
   }
 };
 #else
 struct Prof {
   __device__ __forceinline__ void start(bool) {}
   __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void count(int) {}
+  __device__ __forceinline__ void flush(int, int) {}
 };
 #endif
 // worker phases
@@ -92,7 +114,7 @@ enum { PW_INPUT = 0, PW_VEC, PW_LN1, PW_WAIT_D1, PW_E1, PW_WAIT_O, PW_E3, PW_WAI
        PM_WAIT_A0 = 32, PM_QKV, PM_WAIT_STAGED, PM_S, PM_WAIT_P, PM_PV, PM_WAIT_OD7, PM_OUT, PM_WAIT_A0B, PM_FF1, PM_WAIT_H, PM_FF2, PM_RINGWAIT };
 
 struct LayerArgs {
-  CUtensorMap tm_qkv, tm_out, tm_w1, tm_w2;
+  CUtensorMap tm_qkv, tm_out, tm_w1, tm_w2;     // tm_out: box [256 rows x 32 cols], 64B swizzle (one head's K slice of Wout)
   const float *ln1_g, *ln1_b, *b_out, *ln2_g, *ln2_b, *b_ff1, *b_ff2;
   uint64_t pad_;
 };
@@ -104,7 +126,8 @@ struct FusedArgs {
   LayerArgs layer[MAX_DEPTH];
   const void* in;
   void* out;
-  const float* pos;          // [n_tok, 256] or nullptr
+  const float* pos;          // [n_tok, 256] or nullptr (IO_ROWS_F32)
+  const float* pos_t;        // IO_NCHW_BF16: the same table channel-major [256, POS_LD] (a warp's rows = consecutive tokens read one line)
   int ld_in, ld_out;         // IO_ROWS_F32 row strides (elements)
   int n_seq, n_tok, slot, slot_log2, spt, n_tiles, n_chunks, depth;
 };
@@ -125,6 +148,47 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float u = x * fmaf(x * x, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
   const float hx = 0.5f * x;
   return fmaf(hx, fast_tanh(u), hx);
+}
+// Packed bf16x2 arithmetic for the two MUFU-heavy epilogues (softmax exponentials, tanh-GELU).  Their results are rounded to
+// bf16 anyway (P and gelu(h) are tensor-core operands), so evaluating the transcendental on a bf16 pair halves the MUFU work
+// (16 results / clk / SM -> 32) and the surrounding multiply-adds.  -DAVF_FUSED_PACKED=0 restores the fp32 evaluation.
+#ifndef AVF_FUSED_PACKED
+#define AVF_FUSED_PACKED 1
+#endif
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
+  uint32_t r;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+  uint32_t r;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t fma_bf16x2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// tanh-GELU of a bf16 pair: 0.5x(1 + tanh(x(c0 + c1 x^2))), 5 packed multiply-adds + 1 MUFU
+__device__ __forceinline__ uint32_t gelu_bf16x2(uint32_t x) {
+  constexpr uint32_t C0 = 0x3F4C3F4Cu;      // 0.796875  ~ sqrt(2/pi)
+  constexpr uint32_t C1 = 0x3D123D12u;      // 0.035645  ~ sqrt(2/pi) * 0.044715
+  constexpr uint32_t HALF = 0x3F003F00u;
+  const uint32_t x2 = mul_bf16x2(x, x);
+  const uint32_t u = mul_bf16x2(x, fma_bf16x2(x2, C1, C0));
+  const uint32_t hx = mul_bf16x2(x, HALF);
+  return fma_bf16x2(hx, tanh_bf16x2(u), hx);
 }
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -353,42 +417,56 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       // so the 32-value register block is never merged across a divergent branch (which used to put it on the stack).
       const float vmul = valid ? 1.f : 0.f;
       const int t_safe = valid ? t_in_seq : 0, seq_safe = valid ? seq_in_tile : 0;
-      const float* pp = a.pos != nullptr ? a.pos + t_safe * DIM + g * CW : nullptr;
+      const float* pp = (IO == IO_ROWS_F32 && a.pos != nullptr) ? a.pos + t_safe * DIM + g * CW : nullptr;
+      const float* ppt = a.pos_t + size_t(g * CW) * POS_LD + t_safe;
       if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
       const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(seq_safe * DIM + g * CW) * n_tok + t_safe;
       const float* src32 = static_cast<const float*>(a.in) + ((size_t(tile) * spt + seq_safe) * n_tok + t_safe) * a.ld_in + g * CW;
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
-        float4 p4[8];
-        if (pp != nullptr) {                          // requested first: the L2 round trip overlaps the 32 shared-memory reads below
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp + c0) + j);
-        }
         float x[32];
         if constexpr (IO == IO_NCHW_BF16) {
+          // positional values first (coalesced: the lanes of a warp are consecutive tokens of one channel row), the 32
+          // shared-memory reads of the staged frame overlap their L1/L2 round trip
+          float p[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __bfloat162float(src16[(c0 + j) * n_tok]);
+          for (int j = 0; j < 32; ++j) p[j] = __ldg(ppt + (c0 + j) * POS_LD);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (__bfloat162float(src16[(c0 + j) * n_tok]) + p[j]) * vmul;
         } else {
+          float4 p4[8];
+          if (pp != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) p4[j] = __ldg(reinterpret_cast<const float4*>(pp + c0) + j);
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 x4 = *reinterpret_cast<const float4*>(src32 + c0 + j);
             x[j] = x4.x; x[j + 1] = x4.y; x[j + 2] = x4.z; x[j + 3] = x4.w;
           }
-        }
-        if (pp != nullptr) {
+          if (pp != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
+            for (int j = 0; j < 8; ++j) {
+              x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
+            }
           }
-        }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] *= vmul;
+          for (int j = 0; j < 32; ++j) x[j] *= vmul;
+        }
         st.add(x, c0 == 0);
         tmem_st32(tl + TM_X + g * CW + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
       }
       tmem_st_wait();
       w.finish_stats(st, mean, rstd);
-      if constexpr (IO == IO_NCHW_BF16) bar_sync(5, NUM_WORKERS);   // every worker has read its part of the staged frames out of A0
+      if constexpr (IO == IO_NCHW_BF16) {
+        // the previous tile's output store must have finished READING A1 before this tile's attention writes it again: waited
+        // for here (one thread, ordered for everybody by the barrier below) instead of right after issuing it
+        if (threadIdx.x == WORKER_T0) {
+          bulk_wait_read0();
+          mbar_arrive(&bars[B_OUT_READ]);   // ... and before the QKV ring (which lives in A1) is refilled for this tile
+        }
+        bar_sync(5, NUM_WORKERS);   // every worker has read its part of the staged frames out of A0
+      }
     }
     pf.mark(PW_INPUT);
 
@@ -437,7 +515,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           w.arrive(B_STAGED);
           pf.mark(PW_E1);
         }
-        if (h > 0) {             // E3 of head h-1: O / l -> bf16 -> A1 columns [(h-1)*32 + g*OW, +OW)
+        if (h > 0) {             // E3 of head h-1: O / l -> bf16 -> staging buffer (h-1)&1, columns [g*OW, +OW) (A operand of the per-head out-projection)
           mbar_wait(&bars[B_O_FULL], (h - 1) & 1);
           tc_fence_after();
           pf.mark(PW_WAIT_O);
@@ -446,14 +524,20 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           if constexpr (OW == 16) tmem_ld16(tl + TM_O + g * OW, reinterpret_cast<uint32_t(&)[16]>(r[0]));
           else tmem_ld8(tl + TM_O + g * OW, reinterpret_cast<uint32_t(&)[8]>(r[0]));
           tmem_ld_wait();
-          const int col = (h - 1) * DH + g * OW;
-          const int panel = col >> 6, chunk = (col & 63) >> 3;
+#if AVF_FUSED_PACKED
+          {   // l = own + partner's partial row sum of head h-1 (written before their P_READY arrive, which PV -> O_FULL follows)
+            const float* sums = reinterpret_cast<const float*>(smem + OFF_XCH) + ((h - 1) & 1) * (128 * 4) + row * 4 + 2;
+            inv_l = 1.f / (sums[0] + sums[1]);
+          }
+#endif
+          uint8_t* ob = smem + OFF_OST + ((h - 1) & 1) * 8192 + row * 64;
+          const uint32_t sw = uint32_t((row >> 1) & 3);
 #pragma unroll
           for (int c = 0; c < OW / 8; ++c) {
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[c * 8 + j]) * inv_l;
-            *reinterpret_cast<uint4*>(smem + OFF_A1 + panel * 16384 + row * 128 + (((chunk + c) ^ (row & 7)) << 4)) = pack8(y);
+            *reinterpret_cast<uint4*>(ob + ((uint32_t(g * (OW / 8) + c) ^ sw) << 4)) = pack8(y);
           }
           w.arrive(B_O_DRAINED);
           pf.mark(PW_E3);
@@ -483,6 +567,29 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
               mloc = fmaxf(mloc, fmaxf(fmaxf(fmaxf(s[c][0], s[c][1]), fmaxf(s[c][2], s[c][3])), fmaxf(fmaxf(s[c][4], s[c][5]), fmaxf(s[c][6], s[c][7]))));
             }
           }
+#if AVF_FUSED_PACKED
+          // the row maximum first (one exchange; it also orders every S load of the row before any P store — P is written over
+          // the S columns), then 2^(s - max) straight to its final bf16 value, two per MUFU instruction; the partial row sums
+          // (fp32, of the rounded values the MMA will see) meet again in E3 through shared memory, no second barrier
+          pf.mark(PW_E2_EXP);
+          const float mrow = w.exchange_max(mloc);
+          pf.mark(PW_E2_XCH);
+          const float nml = -mrow * sm_scale;            // every row has at least one valid column: mrow is finite
+          float sum_g = 0.f;
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            if (c < my_nc) {
+              uint32_t e[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), fmaf(s[c][2 * j + 1], sm_scale, nml)));
+                sum_g += __uint_as_float(e[j] << 16) + __uint_as_float(e[j] & 0xFFFF0000u);
+              }
+              tmem_st4(tl + TM_S + (my_c0 + c) * 4, e[0], e[1], e[2], e[3]);
+            }
+          }
+          reinterpret_cast<float*>(smem + OFF_XCH)[(h & 1) * (128 * 4) + row * 4 + 2 + g] = sum_g;
+#else
           const float nml = mloc == -INFINITY ? 0.f : -mloc * sm_scale;      // a thread without valid columns contributes zeros
           float sum_g = 0.f;
 #pragma unroll
@@ -505,6 +612,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
               tmem_st4(tl + TM_S + (my_c0 + c) * 4, pack_bf16x2(s[c][0] * f, s[c][1] * f), pack_bf16x2(s[c][2] * f, s[c][3] * f),
                        pack_bf16x2(s[c][4] * f, s[c][5] * f), pack_bf16x2(s[c][6] * f, s[c][7] * f));
           }
+#endif
           // P columns the MMA reads (all 128) but this warp's rows never use: zeros; thread g takes TMEM columns [32g, 32g + 32)
           {
             const int z_lo = g * 32, z_hi = z_lo + 32, w_lo = c_lo * 4, w_hi = c_hi * 4;
@@ -551,6 +659,16 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           tmem_ld_wait();
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
+#if AVF_FUSED_PACKED
+            uint32_t yk[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 8 + j);
+              yk[j / 2] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[ch * 8 + j]) + b4.x, __uint_as_float(r[ch * 8 + j + 1]) + b4.y));
+              yk[j / 2 + 1] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[ch * 8 + j + 2]) + b4.z, __uint_as_float(r[ch * 8 + j + 3]) + b4.w));
+            }
+            *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = make_uint4(yk[0], yk[1], yk[2], yk[3]);
+#else
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; j += 4) {
@@ -561,6 +679,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
               y[j + 3] = gelu_fast(__uint_as_float(r[ch * 8 + j + 3]) + b4.w);
             }
             *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
+#endif
           }
         }
         w.arrive(B_H_READY + b);
@@ -598,16 +717,14 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         bar_sync(5, NUM_WORKERS);
         if (threadIdx.x == WORKER_T0) {
           __nv_bfloat16* gdst = static_cast<__nv_bfloat16*>(a.out) + size_t(tile) * spt * n_tok * DIM;
-          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(seqs_here) * n_tok * DIM * 2);
-          bulk_wait_read0();     // A1 is written again by the next tile's attention (ordered by the bar_sync after its input sweep)
+          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(seqs_here) * n_tok * DIM * 2);   // read completion: see the next tile's input sweep
         }
       }
     }
     pf.mark(PW_OUTPUT);
-#ifdef AVF_FUSED_PROF
-    if (pf.on) g_prof[PW_TILES] += 1;
-#endif
+    pf.count(PW_TILES);
   }
+  pf.flush(0, 32);
   if constexpr (IO == IO_NCHW_BF16) {
     if (threadIdx.x == WORKER_T0) bulk_wait_all0();
   }
@@ -620,7 +737,6 @@ template <int IO>
 __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
   // (one lane only: this loop polls with try_wait between slots, and a whole-warp version — every lane polling and adopting the
   //  issuing lane's observation — measured 7x slower; the MMA warp, which blocks instead of polling, does run warp-wide)
-  constexpr bool leader = true;
   uint32_t it = 0;
   // Input frames of the NEXT tile go into A0 as soon as the MMAs of the current tile are done with it (B_A0_FREE, one
   // completion per tile).  Polled between weight slots so that this thread never blocks on it.
@@ -635,57 +751,44 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     }
     const int seqs_here = min(a.spt, a.n_seq - load_tile * a.spt);
     const uint32_t bytes = uint32_t(seqs_here) * a.n_tok * DIM * 2;
-    if (leader) {
-      mbar_expect_tx(&bars[B_X0_FULL], bytes);
-      bulk_load_1d(smem + OFF_A0, static_cast<const __nv_bfloat16*>(a.in) + size_t(load_tile) * a.spt * a.n_tok * DIM, bytes, &bars[B_X0_FULL]);
-    }
+    mbar_expect_tx(&bars[B_X0_FULL], bytes);
+    bulk_load_1d(smem + OFF_A0, static_cast<const __nv_bfloat16*>(a.in) + size_t(load_tile) * a.spt * a.n_tok * DIM, bytes, &bars[B_X0_FULL]);
     load_tile += gridDim.x;
     need_free = true;
   };
-  auto slot = [&](uint32_t bytes) -> uint8_t* {
-    const uint32_t s = it % RING, ph = (it / RING) & 1;
+  // Slot s is refilled once its previous content has been consumed (per-slot parity bits: the out-projection slices rotate over
+  // slots 2-4, the MLP weights over all five — slots 0-1 alias the Q/K/V staging and are only loaded after the attention MMAs).
+  uint32_t pbits = 0, n_gate = 0;
+  auto poll_wait = [&](uint64_t* bar, uint32_t parity) {
     poll_loader();
     const long long t0 = clock64();
-    while (!mbar_try_wait(&bars[B_RING_EMPTY + s], ph ^ 1)) {
+    while (!mbar_try_wait(bar, parity)) {
       poll_loader();
       if (clock64() - t0 > 4000000000LL) {
-        printf("avf: fused encoder producer timed out (block %d slot %u)\n", blockIdx.x, it);
+        printf("avf: fused encoder producer timed out (block %d item %u)\n", blockIdx.x, it);
         __trap();
       }
     }
-    if (leader) mbar_expect_tx(&bars[B_RING_FULL + s], bytes);
-    return smem + OFF_RING + s * SLOT_BYTES;
+  };
+  auto load = [&](uint32_t s, const CUtensorMap* tm, int c0, int c1) {
+    poll_wait(&bars[B_RING_EMPTY + s], ((pbits >> s) & 1u) ^ 1u);
+    pbits ^= 1u << s;
+    mbar_expect_tx(&bars[B_RING_FULL + s], SLOT_BYTES);
+    tma_load_2d(smem + OFF_Q + s * SLOT_BYTES, tm, &bars[B_RING_FULL + s], c0, c1);
+    ++it;
   };
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      for (int h = 0; h < HEADS; ++h)
-        for (int kp = 0; kp < 4; ++kp) {
-          uint8_t* d = slot(3 * 32 * 128);
-          uint64_t* fb = &bars[B_RING_FULL + it % RING];
-          for (int s3 = 0; s3 < 3; ++s3) if (leader) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
-          ++it;
-        }
-      for (int kp = 0; kp < 4; ++kp)
-        for (int nh = 0; nh < 2; ++nh) {
-          uint8_t* d = slot(SLOT_BYTES);
-          if (leader) tma_load_2d(d, &L.tm_out, &bars[B_RING_FULL + it % RING], kp * 64, nh * 128);
-          ++it;
-        }
+      for (int h = 0; h < HEADS; ++h) load(RING_LO + h % (RING - RING_LO), &L.tm_out, h * DH, 0);   // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
+      poll_wait(&bars[B_QKV_FREE], (n_gate++) & 1);          // the attention MMAs are done with the Q/K/V staging = slots 0-1
+      uint32_t m = 0;
       auto ff1 = [&](int c) {
-        for (int kp = 0; kp < 4; ++kp) {
-          uint8_t* d = slot(SLOT_BYTES);
-          if (leader) tma_load_2d(d, &L.tm_w1, &bars[B_RING_FULL + it % RING], kp * 64, c * 128);
-          ++it;
-        }
+        for (int kp = 0; kp < 4; ++kp) load((m++) % RING, &L.tm_w1, kp * 64, c * 128);
       };
       auto ff2 = [&](int c) {
         for (int kp = 0; kp < 2; ++kp)
-          for (int nh = 0; nh < 2; ++nh) {
-            uint8_t* d = slot(SLOT_BYTES);
-            if (leader) tma_load_2d(d, &L.tm_w2, &bars[B_RING_FULL + it % RING], c * 128 + kp * 64, nh * 128);
-            ++it;
-          }
+          for (int nh = 0; nh < 2; ++nh) load((m++) % RING, &L.tm_w2, c * 128 + kp * 64, nh * 128);
       };
       ff1(0);
       if (a.n_chunks > 1) ff1(1);
@@ -693,6 +796,34 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
         ff2(c);
         if (c + 2 < a.n_chunks) ff1(c + 2);
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// QKV weight producer (one thread of its own warp): the 4 x 12 KB ring inside A1
+// ---------------------------------------------------------------------------------------------
+template <int IO>
+__device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
+  uint32_t qit = 0, n_free = 0, n_read = 0;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    // A1 doubles as the NCHW output staging: the previous tile's bulk store must have read it (signalled after this tile's input sweep)
+    if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_OUT_READ], (n_read++) & 1);
+    for (int l = 0; l < a.depth; ++l) {
+      const LayerArgs& L = a.layer[l];
+      if (!first) mbar_wait(&bars[B_A1_FREE], (n_free++) & 1);   // the previous layer's last FF2 MMAs have read the GELU buffers in A1
+      first = false;
+      for (int h = 0; h < HEADS; ++h)
+        for (int kp = 0; kp < 4; ++kp) {
+          const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
+          mbar_wait(&bars[B_QR_EMPTY + s], ph ^ 1);
+          uint64_t* fb = &bars[B_QR_FULL + s];
+          uint8_t* d = smem + OFF_QRING + s * QSLOT_BYTES;
+          mbar_expect_tx(fb, QSLOT_BYTES);
+          for (int s3 = 0; s3 < 3; ++s3) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
+          ++qit;
+        }
     }
   }
 }
@@ -706,45 +837,56 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   const bool leader = elect_one();
   const uint32_t a0 = smem_u32(smem + OFF_A0), a1 = smem_u32(smem + OFF_A1);
   const uint32_t qs = smem_u32(smem + OFF_Q), ks = smem_u32(smem + OFF_K), vs = smem_u32(smem + OFF_V);
-  const uint32_t ring = smem_u32(smem + OFF_RING);
+  const uint32_t ring = smem_u32(smem + OFF_Q), qring = smem_u32(smem + OFF_QRING), ost = smem_u32(smem + OFF_OST);
   const int kmax = 128;                        // S / P span the whole tile: sequences sit in power-of-two row slots
   const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, kmax), id_pv = make_idesc_bf16(128, DH, 0, 1),
-                 id_128 = make_idesc_bf16(128, 128);
-  uint32_t it = 0, n_a0 = 0, n_hready[2] = {0, 0};
+                 id_128 = make_idesc_bf16(128, 128), id_256 = make_idesc_bf16(128, 256);
+  uint32_t cbits = 0, m = 0, qit = 0, n_a0 = 0, n_hready[2] = {0, 0};
   Prof pf;
   pf.start(blockIdx.x == 0 && leader);
   int ring_phase = PM_QKV;
-  auto slot_wait = [&]() -> uint32_t {
-    const uint32_t s = it % RING, ph = (it / RING) & 1;
+  auto slot_wait = [&](uint32_t s) -> uint32_t {     // same slot sequence as producer_main
     pf.mark(ring_phase);
-    mbar_wait(&bars[B_RING_FULL + s], ph);
+    mbar_wait(&bars[B_RING_FULL + s], (cbits >> s) & 1u);
     tc_fence_after();
     pf.mark(PM_RINGWAIT);
     return ring + s * SLOT_BYTES;
   };
-  auto slot_release = [&]() {
-    if (leader) umma_commit(&bars[B_RING_EMPTY + it % RING]);
-    ++it;
+  auto slot_release = [&](uint32_t s) {
+    if (leader) umma_commit(&bars[B_RING_EMPTY + s]);
+    cbits ^= 1u << s;
   };
-  auto qkv = [&]() {                          // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T
+  auto qkv = [&]() {                          // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T, weights from the QKV ring
     for (int kp = 0; kp < 4; ++kp) {
-      const uint32_t sb = slot_wait();
-      const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
+      const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
+      pf.mark(ring_phase);
+      mbar_wait(&bars[B_QR_FULL + s], ph);
+      tc_fence_after();
+      pf.mark(PM_RINGWAIT);
+      const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(qring + s * QSLOT_BYTES);
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
-      slot_release();
+      if (leader) umma_commit(&bars[B_QR_EMPTY + s]);
+      ++qit;
     }
     if (leader) umma_commit(&bars[B_D1_FULL]);
+  };
+  auto outproj = [&](int h) {                 // x += (O_h / l) Wout[:, 32h .. 32h+32)^T   (x + b_out was stored by the workers)
+    const uint32_t s = RING_LO + h % (RING - RING_LO), sb = slot_wait(s);
+    const uint64_t da = desc_sw64(ost + (h & 1) * 8192), db = desc_sw64(sb);
+    if (leader) umma_bf16(tmem + TM_X, da, db, id_256, 1u);
+    if (leader) umma_bf16(tmem + TM_X, da + 2, db + 2, id_256, 1u);
+    slot_release(s);
   };
   bool last_layer = false;
   auto ff1 = [&](int c) {                     // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
     const uint32_t d = tmem + ((c & 1) ? TM_H1 : TM_H0);
     for (int kp = 0; kp < 4; ++kp) {
-      const uint32_t sb = slot_wait();
+      const uint32_t s = (m++) % RING, sb = slot_wait(s);
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (leader) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (kp | k) != 0 ? 1u : 0u);
-      slot_release();
+      slot_release(s);
     }
     if (leader) umma_commit(&bars[B_HACC_FULL + (c & 1)]);
     if (c == a.n_chunks - 1 && last_layer) if (leader) umma_commit(&bars[B_A0_FREE]);
@@ -772,8 +914,16 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         pf.mark(PM_S);
         if (h + 1 < HEADS) qkv();
         pf.mark(PM_QKV);
+        if (h > 0) {                          // O(h-1) is out of TMEM and staged: its slice of the out-projection
+          mbar_wait(&bars[B_O_DRAINED], (h - 1) & 1);
+          tc_fence_after();
+          pf.mark(PM_WAIT_OD7);
+          ring_phase = PM_OUT;
+          outproj(h - 1);
+          pf.mark(PM_OUT);
+          ring_phase = PM_QKV;
+        }
         mbar_wait(&bars[B_P_READY], h & 1);
-        if (h > 0) mbar_wait(&bars[B_O_DRAINED], (h - 1) & 1);
         tc_fence_after();
         pf.mark(PM_WAIT_P);
         for (int k = 0; k < kmax / 16; ++k)   // O[128 x 32] = P V_h   (A from TMEM, B MN-major)
@@ -785,15 +935,10 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       tc_fence_after();
       pf.mark(PM_WAIT_OD7);
       ring_phase = PM_OUT;
-      for (int kp = 0; kp < 4; ++kp)          // x += attn Wout^T  (x + b_out was stored by the workers)
-        for (int nh = 0; nh < 2; ++nh) {
-          const uint32_t sb = slot_wait();
-          const uint64_t da = make_desc_sw128_kmajor(a1 + kp * 16384), db = make_desc_sw128_kmajor(sb);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
-          slot_release();
-        }
+      outproj(HEADS - 1);
       if (leader) umma_commit(&bars[B_X1_FULL]);
+      if (leader) umma_commit(&bars[B_QKV_FREE]);
+      m = 0;
       pf.mark(PM_OUT);
 
       mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
@@ -811,11 +956,11 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         ring_phase = PM_FF2;
         for (int kp = 0; kp < 2; ++kp)        // x += gelu(H_c) W2[:, c*128..]^T
           for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t sb = slot_wait();
+            const uint32_t s = (m++) % RING, sb = slot_wait(s);
             const uint64_t da = make_desc_sw128_kmajor(a1 + b * 32768 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
             for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
-            slot_release();
+            slot_release(s);
           }
         pf.mark(PM_FF2);
         ring_phase = PM_FF1;
@@ -825,8 +970,10 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         }
       }
       if (leader) umma_commit(&bars[B_X2_FULL]);
+      if (leader) umma_commit(&bars[B_A1_FREE]);
     }
   }
+  pf.flush(32, 64);
 }
 
 template <int IO>
@@ -867,6 +1014,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
     if (lane == 0) producer_main<IO>(a, smem, bars);
   } else if (warp == 1) {
     mma_main(a, smem, bars, tmem);
+  } else if (warp == 2) {
+    if (lane == 0) qkv_producer_main<IO>(a, smem, bars);
   } else {
     worker_main<IO>(a, smem, bars, tmem);
   }
@@ -874,6 +1023,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// pos [n_tok, 256] -> pos_t [256, POS_LD] (one tiny launch in front of the fused kernel; 50 KB)
+__global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restrict__ pos, float* __restrict__ pos_t, int n_tok) {
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 6), t = threadIdx.x & 63;
+  pos_t[c * POS_LD + t] = t < n_tok ? pos[t * DIM + c] : 0.f;
 }
 
 int sm_count_cached() {
@@ -908,15 +1063,22 @@ bool encoder_fused_supported(const avf_stack_shape* s) {
 }
 
 // io_kind 0: in/out are NCHW bf16 maps [n_seq, 256, n_tok] (pos required); 1: fp32 token rows with strides ld_in / ld_out.
+size_t encoder_fused_scratch_bytes() { return size_t(DIM) * POS_LD * sizeof(float); }
+
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
-                  const float* pos, cudaStream_t st) {
+                  const float* pos, void* scratch, cudaStream_t st) {
   AVF_REQUIRE(encoder_fused_supported(s), AVF_EUNSUPPORTED, "fused encoder: unsupported shape dim=%d heads=%d dh=%d mlp=%d n_tok=%d depth=%d",
               s->dim, s->heads, s->dim_head, s->mlp_dim, s->n_tok, s->depth);
-  AVF_REQUIRE(io_kind == IO_ROWS_F32 || pos != nullptr, AVF_EINVAL, "fused encoder: NCHW input needs the positional embedding");
+  AVF_REQUIRE(io_kind == IO_ROWS_F32 || (pos != nullptr && scratch != nullptr), AVF_EINVAL,
+              "fused encoder: NCHW input needs the positional embedding and the scratch buffer");
   AVF_REQUIRE(io_kind == IO_NCHW_BF16 || (ld_in % 4 == 0 && ld_out % 4 == 0), AVF_EINVAL, "fused encoder: row strides must be multiples of 4");
   static thread_local FusedArgs a;      // ~2 KB of tensor maps + pointers, passed by value (__grid_constant__) per launch
   static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
-  a.in = in; a.out = out; a.pos = pos; a.ld_in = ld_in; a.ld_out = ld_out;
+  a.in = in; a.out = out; a.pos = pos; a.pos_t = static_cast<const float*>(scratch); a.ld_in = ld_in; a.ld_out = ld_out;
+  if (io_kind == IO_NCHW_BF16) {
+    pos_transpose_kernel<<<DIM / 4, 256, 0, st>>>(pos, static_cast<float*>(scratch), s->n_tok);
+    AVF_LAUNCH_CHECK("pos_transpose_kernel");
+  }
   a.n_seq = s->n_seq; a.n_tok = s->n_tok;
   a.slot = 16; a.slot_log2 = 4;
   while (a.slot < s->n_tok) { a.slot *= 2; ++a.slot_log2; }
@@ -928,7 +1090,7 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
     LayerArgs& A = a.layer[l];
     int e;
     if ((e = make_tmap_bf16_2d(&A.tm_qkv, L[l].w_qkv, 3 * inner, DIM, DIM, 32))) return e;
-    if ((e = make_tmap_bf16_2d(&A.tm_out, L[l].w_out, DIM, inner, inner, 128))) return e;
+    if ((e = make_tmap_bf16_2d(&A.tm_out, L[l].w_out, DIM, inner, inner, 256, DH))) return e;
     if ((e = make_tmap_bf16_2d(&A.tm_w1, L[l].w_ff1, s->mlp_dim, DIM, DIM, 128))) return e;
     if ((e = make_tmap_bf16_2d(&A.tm_w2, L[l].w_ff2, DIM, s->mlp_dim, s->mlp_dim, 128))) return e;
     A.ln1_g = L[l].ln1_gamma; A.ln1_b = L[l].ln1_beta; A.b_out = L[l].b_out;
@@ -940,7 +1102,8 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
     AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_ROWS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     configured = true;
   }
-  const int grid = min(a.n_tiles, sm_count_cached());
+  const int cap = sm_cap();
+  const int grid = min(a.n_tiles, cap > 0 ? min(cap, sm_count_cached()) : sm_count_cached());
   if (io_kind == IO_NCHW_BF16)
     encoder_fused_kernel<IO_NCHW_BF16><<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(a);
   else

@@ -10,10 +10,12 @@ graph branches.  No tracing compiler is involved: the captured work is exactly t
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 
+from . import _lib
 from .encoder import Transformer
 
 
@@ -32,9 +34,17 @@ class GraphedHotPath:
     """model.hot_path(...) captured for fixed input shapes.  Inputs are copied into static buffers (device-to-device or
     host-to-device), outputs are the graph's static tensors (valid until the next replay)."""
 
-    def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor):
+    def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor, sm_split=None):
+        """sm_split = (sformer_sms, chain_sms): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the TFormer /
+        AU_former / fusion-head chain, whose persistent GEMMs are capped at `chain_sms` CTAs (every persistent CTA of either
+        family owns a whole SM, so the two grids partition the GPU).  None = the two run one after the other on all SMs.
+        Default from the environment variable AVF_SM_SPLIT="s,c"."""
         if model.training:
             raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
+        if sm_split is None and os.environ.get("AVF_SM_SPLIT"):
+            sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
+        self.sm_split = tuple(sm_split) if sm_split else None
+        self.side2 = torch.cuda.Stream()
         self.model = model
         self.stage3, self.frame = stage3.clone(), frame.clone()
         self.audio = audio.float().clone()
@@ -51,6 +61,15 @@ class GraphedHotPath:
         cur = torch.cuda.current_stream()
         n_clips = self.frame.numel() // (vm.t_former.num_patches * vm.t_former.dim)
         fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=self.frame.device)
+        L = _lib.lib()
+        old_cap = 0
+        if self.sm_split is not None:
+            # branch: the SFormer (independent of the chain below) on its own share of the SMs
+            self.side2.wait_stream(cur)
+            old_cap = L.avf_set_sm_cap(self.sm_split[0])
+            with torch.cuda.stream(self.side2):
+                s_out = vm.s_former.sformer(self.stage3)
+            L.avf_set_sm_cap(self.sm_split[1])
         # branch: the audio AU_former is independent of everything up to the fusion head
         self.side.wait_stream(cur)
         with torch.cuda.stream(self.side):
@@ -59,7 +78,11 @@ class GraphedHotPath:
         m.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         cur.wait_stream(self.side)
         out21, dec = m.au_head.logits21_(fused, n_clips, True)
-        s_out = vm.s_former.sformer(self.stage3)
+        if self.sm_split is not None:
+            L.avf_set_sm_cap(old_cap)
+            cur.wait_stream(self.side2)
+        else:
+            s_out = vm.s_former.sformer(self.stage3)
         return s_out, out21, dec
 
     def replay(self, stage3: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None, audio: Optional[torch.Tensor] = None):
