@@ -46,7 +46,7 @@ constexpr int QRING = 4, QSLOT_BYTES = 12288;   // QKV ring: one slot = one 64-w
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int OFF_A0 = 0;                          // 64 KB  LN output [128 x 256] bf16, 4 K-panels; also the NCHW input staging
-constexpr int OFF_A1 = 65536;                      // 64 KB  attention phase: O_h staging + QKV ring; MLP: 2 x GELU(hidden chunk); NCHW output staging
+constexpr int OFF_A1 = 65536;                      // 64 KB  O_h staging + QKV ring (both ahead of the attention phase); NCHW output staging
 constexpr int OFF_OST = OFF_A1;                    //   2 x 8 KB  O_h / l  [128 x 32] K-major SW64, double buffered
 constexpr int OFF_QRING = OFF_A1 + 16384;          //   4 x 12 KB QKV weight ring
 constexpr int OFF_Q = 131072;                      // 8 KB   Q_h [128 x 32] K-major SW64
@@ -57,7 +57,8 @@ static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguo
 constexpr int OFF_XCH = OFF_RING + (RING - RING_LO) * SLOT_BYTES;   // row exchange [2][128][4] floats
 constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors (LN affine, biases), fp32
 constexpr int V_LN1G = 0, V_LN1B = 256, V_BOUT = 512, V_LN2G = 768, V_LN2B = 1024, V_BFF2 = 1280, V_BFF1 = 1536;
-constexpr int OFF_BAR = OFF_VEC + (V_BFF1 + MAX_MLP) * 4;
+constexpr int V_B16 = V_BFF1 + MAX_MLP;             // then bf16 copies of the LayerNorm affine vectors: [ln1_g | ln1_b | ln2_g | ln2_b] x 256
+constexpr int OFF_BAR = OFF_VEC + (V_B16 + 512) * 4;
 constexpr int SMEM_USED = OFF_BAR + 512;
 constexpr int SMEM_ALLOC = SMEM_USED + 1024;       // slack for the 1024-byte alignment of the base
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
@@ -127,7 +128,8 @@ struct FusedArgs {
   const void* in;
   void* out;
   const float* pos;          // [n_tok, 256] or nullptr (IO_ROWS_F32)
-  const float* pos_t;        // IO_NCHW_BF16: the same table channel-major [256, POS_LD] (a warp's rows = consecutive tokens read one line)
+  const float* pos_t;        // IO_NCHW_BF16: the same table as [256 / 4][POS_LD tokens][4 channels]: one 16-byte load per 4 channels,
+                             // and the lanes of a warp (consecutive tokens) read consecutive 16-byte words
   int ld_in, ld_out;         // IO_ROWS_F32 row strides (elements)
   int n_seq, n_tok, slot, slot_log2, spt, n_tiles, n_chunks, depth;
 };
@@ -198,6 +200,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
@@ -345,6 +354,17 @@ struct Worker {
       const int chunk0 = (col0 & 63) >> 3;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
+#if AVF_FUSED_PACKED
+        // (x - mean) * rstd in fp32, the affine part on bf16 pairs (gamma / beta pre-rounded to bf16 in shared memory)
+        const __nv_bfloat16* v16 = reinterpret_cast<const __nv_bfloat16*>(vec + V_B16) + (v_gamma == V_LN1G ? 0 : 512) + col0 + ch * 8;
+        const uint4 gm = *reinterpret_cast<const uint4*>(v16), bt = *reinterpret_cast<const uint4*>(v16 + 256);
+        uint4 pk;
+        pk.x = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8], rstd, nmr), fmaf(x[ch * 8 + 1], rstd, nmr)), gm.x, bt.x);
+        pk.y = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 2], rstd, nmr), fmaf(x[ch * 8 + 3], rstd, nmr)), gm.y, bt.y);
+        pk.z = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 4], rstd, nmr), fmaf(x[ch * 8 + 5], rstd, nmr)), gm.z, bt.z);
+        pk.w = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 6], rstd, nmr), fmaf(x[ch * 8 + 7], rstd, nmr)), gm.w, bt.w);
+        *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pk;
+#else
         float y[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
@@ -356,6 +376,7 @@ struct Worker {
           y[j + 3] = fmaf(fmaf(x[ch * 8 + j + 3], rstd, nmr), gm.w, bt.w);
         }
         *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
+#endif
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -399,7 +420,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
   // does any chunk of this thread contain a column outside some row's window?  (interior chunks need no mask)
   const bool warp_one_seq = s0 == s1;
   const float sm_scale = 1.4426950408889634f * rsqrtf(float(DH));
-  uint32_t n_x0 = 0, n_x1 = 0, n_x2 = 0, n_hacc0 = 0, n_hacc1 = 0, n_hfree0 = 0, n_hfree1 = 0;
+  uint32_t n_x0 = 0, n_x1 = 0, n_x2 = 0, n_hacc0 = 0, n_hacc1 = 0;
   bool vec_loaded = false;
   Prof pf;
   pf.start(blockIdx.x == 0 && wt == 0);
@@ -413,12 +434,11 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
     float mean, rstd;
     {
       Worker::Stats st{0.f, 0.f, 0.f};
-      // Branch-free: padding rows (and sequences beyond the end of the batch) read a valid location and are multiplied by zero,
-      // so the 32-value register block is never merged across a divergent branch (which used to put it on the stack).
-      const float vmul = valid ? 1.f : 0.f;
+      // Branch-free: padding rows (and sequences beyond the end of the batch) read a valid location, i.e. they carry a copy of a
+      // real token.  Nothing ever looks at them: as keys they are outside every row's softmax window, as rows they are not stored.
       const int t_safe = valid ? t_in_seq : 0, seq_safe = valid ? seq_in_tile : 0;
       const float* pp = (IO == IO_ROWS_F32 && a.pos != nullptr) ? a.pos + t_safe * DIM + g * CW : nullptr;
-      const float* ppt = a.pos_t + size_t(g * CW) * POS_LD + t_safe;
+      const float4* ppt = reinterpret_cast<const float4*>(a.pos_t) + size_t(g * CW / 4) * POS_LD + t_safe;
       if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_X0_FULL], (n_x0++) & 1);
       const __nv_bfloat16* src16 = reinterpret_cast<const __nv_bfloat16*>(smem + OFF_A0) + size_t(seq_safe * DIM + g * CW) * n_tok + t_safe;
       const float* src32 = static_cast<const float*>(a.in) + ((size_t(tile) * spt + seq_safe) * n_tok + t_safe) * a.ld_in + g * CW;
@@ -428,11 +448,16 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         if constexpr (IO == IO_NCHW_BF16) {
           // positional values first (coalesced: the lanes of a warp are consecutive tokens of one channel row), the 32
           // shared-memory reads of the staged frame overlap their L1/L2 round trip
-          float p[32];
+          float4 p[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) p[j] = __ldg(ppt + (c0 + j) * POS_LD);
+          for (int j = 0; j < 8; ++j) p[j] = __ldg(ppt + (c0 / 4 + j) * POS_LD);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (__bfloat162float(src16[(c0 + j) * n_tok]) + p[j]) * vmul;
+          for (int j = 0; j < 8; ++j) {
+            x[4 * j] = __bfloat162float(src16[(c0 + 4 * j) * n_tok]) + p[j].x;
+            x[4 * j + 1] = __bfloat162float(src16[(c0 + 4 * j + 1) * n_tok]) + p[j].y;
+            x[4 * j + 2] = __bfloat162float(src16[(c0 + 4 * j + 2) * n_tok]) + p[j].z;
+            x[4 * j + 3] = __bfloat162float(src16[(c0 + 4 * j + 3) * n_tok]) + p[j].w;
+          }
         } else {
           float4 p4[8];
           if (pp != nullptr) {
@@ -450,8 +475,6 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
               x[4 * j] += p4[j].x; x[4 * j + 1] += p4[j].y; x[4 * j + 2] += p4[j].z; x[4 * j + 3] += p4[j].w;
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] *= vmul;
         }
         st.add(x, c0 == 0);
         tmem_st32(tl + TM_X + g * CW + c0, reinterpret_cast<const uint32_t(&)[32]>(x));
@@ -478,6 +501,9 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         for (int i = wt; i < DIM; i += NUM_WORKERS) {
           vs[V_LN1G + i] = L.ln1_g[i]; vs[V_LN1B + i] = L.ln1_b[i]; vs[V_BOUT + i] = L.b_out[i];
           vs[V_LN2G + i] = L.ln2_g[i]; vs[V_LN2B + i] = L.ln2_b[i]; vs[V_BFF2 + i] = L.b_ff2[i];
+          __nv_bfloat16* v16 = reinterpret_cast<__nv_bfloat16*>(vs + V_B16);
+          v16[i] = __float2bfloat16_rn(L.ln1_g[i]); v16[256 + i] = __float2bfloat16_rn(L.ln1_b[i]);
+          v16[512 + i] = __float2bfloat16_rn(L.ln2_g[i]); v16[768 + i] = __float2bfloat16_rn(L.ln2_b[i]);
         }
         for (int i = wt; i < a.n_chunks * 128; i += NUM_WORKERS) vs[V_BFF1 + i] = L.b_ff1[i];
         bar_sync(5, NUM_WORKERS);
@@ -635,54 +661,40 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       pf.mark(PW_LN2);
 
       // ---- MLP: per 128-column chunk of the hidden layer, bias + tanh-GELU -> bf16 A operand ---------------------
+      // The bf16 result goes back INTO the accumulator's TMEM columns (like P over S): thread g turns its fp32 columns
+      // [g*HW, g*HW + HW) of the chunk into HW/2 packed columns at [g*HW, g*HW + HW/2) — columns it has already read — and the
+      // second MLP GEMM takes its A operand from TMEM.  No shared-memory buffer, no generic->async proxy fence, and half of the
+      // MLP's shared-memory operand traffic is gone (the tensor core re-reads A for every 16-wide k-step).
 #pragma unroll 1
       for (int c = 0; c < a.n_chunks; ++c) {
         const int b = c & 1;
-        if (b == 0) {
-          mbar_wait(&bars[B_HACC_FULL], (n_hacc0++) & 1);
-          if (c >= 2) mbar_wait(&bars[B_HBUF_FREE], (n_hfree0++) & 1);
-        } else {
-          mbar_wait(&bars[B_HACC_FULL1], (n_hacc1++) & 1);
-          if (c >= 2) mbar_wait(&bars[B_HBUF_FREE1], (n_hfree1++) & 1);
-        }
+        if (b == 0) mbar_wait(&bars[B_HACC_FULL], (n_hacc0++) & 1);
+        else mbar_wait(&bars[B_HACC_FULL1], (n_hacc1++) & 1);
         tc_fence_after();
         pf.mark(PW_WAIT_HACC);
         constexpr int HW = 128 / NSPLIT;                   // hidden columns per thread: 64 or 32
+        const uint32_t hbase = tl + (b ? TM_H1 : TM_H0) + g * HW;
 #pragma unroll
         for (int c0 = 0; c0 < HW; c0 += 32) {
-          const int hc = g * HW + c0;                      // column within the 128-wide chunk
-          const float* bias = vec + V_BFF1 + c * 128 + hc;
-          uint8_t* dst = smem + OFF_A1 + b * 32768 + (hc >> 6) * 16384 + row * 128;
-          const int chunk0 = (hc & 63) >> 3;
-          uint32_t r[32];
-          tmem_ld32(tl + (b ? TM_H1 : TM_H0) + hc, r);
+          const float* bias = vec + V_BFF1 + c * 128 + g * HW + c0;
+          uint32_t r[32], yk[16];
+          tmem_ld32(hbase + c0, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
 #if AVF_FUSED_PACKED
-            uint32_t yk[4];
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 8 + j);
-              yk[j / 2] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[ch * 8 + j]) + b4.x, __uint_as_float(r[ch * 8 + j + 1]) + b4.y));
-              yk[j / 2 + 1] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[ch * 8 + j + 2]) + b4.z, __uint_as_float(r[ch * 8 + j + 3]) + b4.w));
-            }
-            *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = make_uint4(yk[0], yk[1], yk[2], yk[3]);
+            yk[j / 2] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y));
+            yk[j / 2 + 1] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w));
 #else
-            float y[8];
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias + ch * 8 + j);
-              y[j] = gelu_fast(__uint_as_float(r[ch * 8 + j]) + b4.x);
-              y[j + 1] = gelu_fast(__uint_as_float(r[ch * 8 + j + 1]) + b4.y);
-              y[j + 2] = gelu_fast(__uint_as_float(r[ch * 8 + j + 2]) + b4.z);
-              y[j + 3] = gelu_fast(__uint_as_float(r[ch * 8 + j + 3]) + b4.w);
-            }
-            *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
+            yk[j / 2] = pack_bf16x2(gelu_fast(__uint_as_float(r[j]) + b4.x), gelu_fast(__uint_as_float(r[j + 1]) + b4.y));
+            yk[j / 2 + 1] = pack_bf16x2(gelu_fast(__uint_as_float(r[j + 2]) + b4.z), gelu_fast(__uint_as_float(r[j + 3]) + b4.w));
 #endif
           }
+          tmem_st16(hbase + c0 / 2, yk);
         }
-        w.arrive(B_H_READY + b);
+        tmem_st_wait();
+        w.arrive_tmem_only(B_H_READY + b);
         pf.mark(PW_GELU);
       }
 
@@ -805,15 +817,12 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
 // ---------------------------------------------------------------------------------------------
 template <int IO>
 __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
-  uint32_t qit = 0, n_free = 0, n_read = 0;
-  bool first = true;
+  uint32_t qit = 0, n_read = 0;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     // A1 doubles as the NCHW output staging: the previous tile's bulk store must have read it (signalled after this tile's input sweep)
     if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_OUT_READ], (n_read++) & 1);
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      if (!first) mbar_wait(&bars[B_A1_FREE], (n_free++) & 1);   // the previous layer's last FF2 MMAs have read the GELU buffers in A1
-      first = false;
       for (int h = 0; h < HEADS; ++h)
         for (int kp = 0; kp < 4; ++kp) {
           const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
@@ -957,20 +966,17 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         for (int kp = 0; kp < 2; ++kp)        // x += gelu(H_c) W2[:, c*128..]^T
           for (int nh = 0; nh < 2; ++nh) {
             const uint32_t s = (m++) % RING, sb = slot_wait(s);
-            const uint64_t da = make_desc_sw128_kmajor(a1 + b * 32768 + kp * 16384), db = make_desc_sw128_kmajor(sb);
+            const uint32_t ta = tmem + (b ? TM_H1 : TM_H0) + uint32_t(kp * 64);       // gelu(H_c) as bf16, 8 columns per 16-wide k-step
+            const uint64_t db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_X + nh * 128, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, 1u);
+            for (int k = 0; k < 4; ++k) if (leader) umma_bf16_ts(tmem + TM_X + nh * 128, ta + uint32_t(k * 8), db + uint64_t(k * 2), id_128, 1u);
             slot_release(s);
           }
         pf.mark(PM_FF2);
         ring_phase = PM_FF1;
-        if (c + 2 < a.n_chunks) {
-          if (leader) umma_commit(&bars[B_HBUF_FREE + b]);
-          ff1(c + 2);
-        }
+        if (c + 2 < a.n_chunks) ff1(c + 2);     // overwrites H_c: in order behind the MMAs above that read it
       }
       if (leader) umma_commit(&bars[B_X2_FULL]);
-      if (leader) umma_commit(&bars[B_A1_FREE]);
     }
   }
   pf.flush(32, 64);
@@ -1025,10 +1031,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// pos [n_tok, 256] -> pos_t [256, POS_LD] (one tiny launch in front of the fused kernel; 50 KB)
+// pos [n_tok, 256] -> pos_t [256 / 4][POS_LD][4] (one tiny launch in front of the fused kernel; 64 KB)
 __global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restrict__ pos, float* __restrict__ pos_t, int n_tok) {
-  const int c = blockIdx.x * 4 + (threadIdx.x >> 6), t = threadIdx.x & 63;
-  pos_t[c * POS_LD + t] = t < n_tok ? pos[t * DIM + c] : 0.f;
+  const int c = blockIdx.x * 4 + (threadIdx.x & 3), t = threadIdx.x >> 2;
+  pos_t[(blockIdx.x * POS_LD + t) * 4 + (threadIdx.x & 3)] = t < n_tok ? pos[t * DIM + c] : 0.f;
 }
 
 int sm_count_cached() {
