@@ -40,8 +40,10 @@ static_assert(NSPLIT == 2 || NSPLIT == 4, "NSPLIT");
 constexpr int WORKER_T0 = 96;              // first worker thread
 constexpr int NUM_WORKERS = 128 * NSPLIT;
 constexpr int NUM_THREADS = WORKER_T0 + NUM_WORKERS;
-constexpr int RING = 5, SLOT_BYTES = 16384;     // main weight ring: slot s at OFF_Q + s * 16 KB; slots 0-1 alias the Q/K/V staging (MLP phase only)
-constexpr int RING_LO = 2;                      // first slot that is free in every phase
+// Main weight ring, 16 KB slots.  Slots 2-4 are free in every phase (out-projection slices rotate over them); the MLP weights
+// rotate over all nine: slots 0-1 alias the Q/K/V staging and slots 5-8 the 64 KB of A1 (O staging + QKV ring), all idle in the
+// MLP phase — 144 KB in flight cover the L2 latency at the MLP's consumption rate (16 KB per 256 tensor cycles).
+constexpr int RING = 9, RING_LO = 2, RING_HI = 5, SLOT_BYTES = 16384;
 constexpr int QRING = 4, QSLOT_BYTES = 12288;   // QKV ring: one slot = one 64-wide K panel of [Wq_h; Wk_h; Wv_h] (3 x 32 rows x 128 B)
 
 // shared memory map (offsets from a 1024-byte aligned base)
@@ -54,7 +56,8 @@ constexpr int OFF_K = OFF_Q + 8192;                // 8 KB   K_h
 constexpr int OFF_V = OFF_K + 8192;                // 2x8 KB V_h [128 tok x 32] MN-major SW64, double buffered
 constexpr int OFF_RING = OFF_V + 16384;            // 3 x 16 KB weight ring (slots 2-4; slots 0-1 = the 32 KB of Q/K/V staging above)
 static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguous from OFF_Q");
-constexpr int OFF_XCH = OFF_RING + (RING - RING_LO) * SLOT_BYTES;   // row exchange [2][128][4] floats
+constexpr int OFF_XCH = OFF_RING + (RING_HI - RING_LO) * SLOT_BYTES;
+__host__ __device__ constexpr int slot_offset(uint32_t s) { return s < RING_HI ? OFF_Q + int(s) * SLOT_BYTES : OFF_A1 + int(s - RING_HI) * SLOT_BYTES; }   // row exchange [2][128][4] floats
 constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors (LN affine, biases), fp32
 constexpr int V_LN1G = 0, V_LN1B = 256, V_BOUT = 512, V_LN2G = 768, V_LN2B = 1024, V_BFF2 = 1280, V_BFF1 = 1536;
 constexpr int V_B16 = V_BFF1 + MAX_MLP;             // then bf16 copies of the LayerNorm affine vectors: [ln1_g | ln1_b | ln2_g | ln2_b] x 256
@@ -786,14 +789,14 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     poll_wait(&bars[B_RING_EMPTY + s], ((pbits >> s) & 1u) ^ 1u);
     pbits ^= 1u << s;
     mbar_expect_tx(&bars[B_RING_FULL + s], SLOT_BYTES);
-    tma_load_2d(smem + OFF_Q + s * SLOT_BYTES, tm, &bars[B_RING_FULL + s], c0, c1);
+    tma_load_2d(smem + slot_offset(s), tm, &bars[B_RING_FULL + s], c0, c1);
     ++it;
   };
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      for (int h = 0; h < HEADS; ++h) load(RING_LO + h % (RING - RING_LO), &L.tm_out, h * DH, 0);   // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
-      poll_wait(&bars[B_QKV_FREE], (n_gate++) & 1);          // the attention MMAs are done with the Q/K/V staging = slots 0-1
+      for (int h = 0; h < HEADS; ++h) load(RING_LO + h % (RING_HI - RING_LO), &L.tm_out, h * DH, 0);   // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
+      poll_wait(&bars[B_QKV_FREE], (n_gate++) & 1);          // the attention MMAs are done with the Q/K/V staging and A1 = slots 0-1, 5-8
       uint32_t m = 0;
       auto ff1 = [&](int c) {
         for (int kp = 0; kp < 4; ++kp) load((m++) % RING, &L.tm_w1, kp * 64, c * 128);
@@ -817,12 +820,15 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
 // ---------------------------------------------------------------------------------------------
 template <int IO>
 __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
-  uint32_t qit = 0, n_read = 0;
+  uint32_t qit = 0, n_free = 0, n_read = 0;
+  bool first = true;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     // A1 doubles as the NCHW output staging: the previous tile's bulk store must have read it (signalled after this tile's input sweep)
     if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_OUT_READ], (n_read++) & 1);
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
+      if (!first) mbar_wait(&bars[B_A1_FREE], (n_free++) & 1);   // the previous layer's MLP weights (ring slots 5-8 live in A1) are consumed
+      first = false;
       for (int h = 0; h < HEADS; ++h)
         for (int kp = 0; kp < 4; ++kp) {
           const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
@@ -846,7 +852,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   const bool leader = elect_one();
   const uint32_t a0 = smem_u32(smem + OFF_A0), a1 = smem_u32(smem + OFF_A1);
   const uint32_t qs = smem_u32(smem + OFF_Q), ks = smem_u32(smem + OFF_K), vs = smem_u32(smem + OFF_V);
-  const uint32_t ring = smem_u32(smem + OFF_Q), qring = smem_u32(smem + OFF_QRING), ost = smem_u32(smem + OFF_OST);
+  const uint32_t smem0 = smem_u32(smem), qring = smem_u32(smem + OFF_QRING), ost = smem_u32(smem + OFF_OST);
   const int kmax = 128;                        // S / P span the whole tile: sequences sit in power-of-two row slots
   const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, kmax), id_pv = make_idesc_bf16(128, DH, 0, 1),
                  id_128 = make_idesc_bf16(128, 128), id_256 = make_idesc_bf16(128, 256);
@@ -859,7 +865,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     mbar_wait(&bars[B_RING_FULL + s], (cbits >> s) & 1u);
     tc_fence_after();
     pf.mark(PM_RINGWAIT);
-    return ring + s * SLOT_BYTES;
+    return smem0 + uint32_t(slot_offset(s));
   };
   auto slot_release = [&](uint32_t s) {
     if (leader) umma_commit(&bars[B_RING_EMPTY + s]);
@@ -881,7 +887,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     if (leader) umma_commit(&bars[B_D1_FULL]);
   };
   auto outproj = [&](int h) {                 // x += (O_h / l) Wout[:, 32h .. 32h+32)^T   (x + b_out was stored by the workers)
-    const uint32_t s = RING_LO + h % (RING - RING_LO), sb = slot_wait(s);
+    const uint32_t s = RING_LO + h % (RING_HI - RING_LO), sb = slot_wait(s);
     const uint64_t da = desc_sw64(ost + (h & 1) * 8192), db = desc_sw64(sb);
     if (leader) umma_bf16(tmem + TM_X, da, db, id_256, 1u);
     if (leader) umma_bf16(tmem + TM_X, da + 2, db + 2, id_256, 1u);
@@ -977,6 +983,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         if (c + 2 < a.n_chunks) ff1(c + 2);     // overwrites H_c: in order behind the MMAs above that read it
       }
       if (leader) umma_commit(&bars[B_X2_FULL]);
+      if (leader) umma_commit(&bars[B_A1_FREE]);
     }
   }
   pf.flush(32, 64);
