@@ -556,7 +556,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
 #if AVF_FUSED_PACKED
           {   // l = own + partner's partial row sum of head h-1 (written before their P_READY arrive, which PV -> O_FULL follows)
             const float* sums = reinterpret_cast<const float*>(smem + OFF_XCH) + ((h - 1) & 1) * (128 * 4) + row * 4 + 2;
-            inv_l = 1.f / (sums[0] + sums[1]);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_l) : "f"(sums[0] + sums[1]));
           }
 #endif
           uint8_t* ob = smem + OFF_OST + ((h - 1) & 1) * 8192 + row * 64;
