@@ -92,6 +92,9 @@ int         avf_set_sm_cap(int cap);
 /* Developer aid: 64 per-phase cycle counters of the fused kernel when the library is built with -DAVF_FUSED_PROF
  * (tools/fused_phases.py); AVF_EUNSUPPORTED otherwise. */
 int         avf_debug_fused_prof(uint64_t* out64, int reset);
+/* Developer aid: `host_mapped_words` = 4 uint32 in pinned (device-visible) host memory, or NULL.  A wait inside the fused
+ * kernel that times out (a protocol bug) writes {block, thread, barrier index, parity} there before it traps. */
+int         avf_debug_set_trap_buffer(void* host_mapped_words);
 
 /* ---- workspace ---------------------------------------------------------------------------- */
 /* Bytes of scratch avf_encoder_stack_fwd needs for this shape/mode (replaces the implicit ATen

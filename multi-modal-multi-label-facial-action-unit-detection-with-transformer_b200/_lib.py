@@ -94,6 +94,7 @@ SIGNATURES = {
                                              ctypes.POINTER(LayerGrads), ctypes.c_int, _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
     "avf_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p]),
     "avf_set_sm_cap": (ctypes.c_int, [ctypes.c_int]),
+    "avf_debug_set_trap_buffer": (ctypes.c_int, [_c_p]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
     "avf_layernorm_bwd_workspace_bytes": (_sz, [_i32, _i32]),

@@ -62,6 +62,7 @@ int attention_bwd_mma_bf16(const void* qkv, const void* dout, void* dqkv, int n_
 // avf_layer_fused.cu: whole encoder stack in one persistent tcgen05 kernel (dim 256, 8 heads x 32)
 bool encoder_fused_supported(const avf_stack_shape* s);
 int fused_prof_read(unsigned long long* out64, int reset);   // phase counters, only with -DAVF_FUSED_PROF
+int fused_set_trap_buffer(void* host_mapped_words);          // 4 host-mapped words a timed-out wait fills in before trapping
 size_t encoder_fused_scratch_bytes();                        // scratch of the NCHW form (channel-major positional table)
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, void* scratch, cudaStream_t st);

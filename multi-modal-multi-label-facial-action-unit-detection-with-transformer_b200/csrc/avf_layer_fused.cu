@@ -137,6 +137,11 @@ struct FusedArgs {
   int n_seq, n_tok, slot, slot_log2, spt, n_tiles, n_chunks, depth;
 };
 
+// Developer aid: a host-mapped word block that the weight producer fills in when its wait for a ring slot times out (a protocol
+// bug) before it traps — the trap poisons the context, but pinned host memory stays readable: {block, thread, barrier index,
+// parity}.  Set with avf_debug_set_trap_buffer (tools/trap_probe.py).
+__device__ unsigned* g_trap_buffer = nullptr;
+
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -780,6 +785,11 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     while (!mbar_try_wait(bar, parity)) {
       poll_loader();
       if (clock64() - t0 > 4000000000LL) {
+        unsigned* tb = g_trap_buffer;
+        if (tb != nullptr) {
+          tb[0] = blockIdx.x; tb[1] = threadIdx.x; tb[2] = (smem_u32(bar) & 1023u) >> 3; tb[3] = parity;
+          __threadfence_system();
+        }
         printf("avf: fused encoder producer timed out (block %d item %u)\n", blockIdx.x, it);
         __trap();
       }
@@ -1054,6 +1064,12 @@ int sm_count_cached() {
 }
 
 }  // namespace
+
+int fused_set_trap_buffer(void* host_mapped_words) {
+  unsigned* p = static_cast<unsigned*>(host_mapped_words);
+  AVF_CUDA(cudaMemcpyToSymbol(g_trap_buffer, &p, sizeof(p)));
+  return 0;
+}
 
 int fused_prof_read(unsigned long long* out64, int reset) {
 #ifdef AVF_FUSED_PROF
