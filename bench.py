@@ -241,7 +241,12 @@ def run_ours(args):
         ms_eager = e0.elapsed_time(e1) / args.steps
 
         # the same step captured once as a CUDA graph (no launch gaps, audio branch on a parallel graph branch): the headline
-        graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"])
+        # (AVF_SM_SPLIT="116,32" runs the persistent SFormer kernel on 116 SMs NEXT TO the TFormer / head chain on the other 32 —
+        #  measured on B200: 1.458 ms against 1.450 ms one after the other, so it is off by default)
+        sm_split = None
+        if os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
+            sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
+        graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split)
 
         def gstep():
             _, out21, _ = graphed.replay()
@@ -347,7 +352,8 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "tensor_frac_whole_step": value / world * hot_path_flops_per_clip(T) / 1e12 / peaks["bf16_tflops_sustained"],
             "breakdown_ms": {"sformer": ms_sformer, "tformer": ms_tformer, "whole_step": ms_step, "whole_step_eager_launches": ms_eager},
-            "launch_mode": "one CUDA-graph replay per step (captured from the library's own kernel launches; gpu_launches counts the kernels inside it)",
+            "launch_mode": "one CUDA-graph replay per step (captured from the library's own kernel launches; gpu_launches counts the kernels inside it)"
+                           + (f"; SFormer kernel on {sm_split[0]} SMs next to the TFormer/head chain on {sm_split[1]} SMs (avf_set_sm_cap)" if sm_split else ""),
             "train": {"metric": "AVFormer hot-path training step clips/sec (fwd + bwd + fused Adam, gradient all-reduce at N>1)",
                       "value": world * TRAIN_CLIPS_PER_GPU / (ms_train * 1e-3), "unit": "clips/s", "ms_per_step": ms_train,
                       "clips_per_gpu": TRAIN_CLIPS_PER_GPU, "n_frames": T, "dtype": "bf16 operands, fp32 master weights / gradients / Adam state",

@@ -41,7 +41,7 @@ class GraphedHotPath:
         Default from the environment variable AVF_SM_SPLIT="s,c"."""
         if model.training:
             raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
-        if sm_split is None and os.environ.get("AVF_SM_SPLIT"):
+        if sm_split is None and os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
             sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
         self.sm_split = tuple(sm_split) if sm_split else None
         self.side2 = torch.cuda.Stream()

@@ -390,13 +390,17 @@ def test_train_mode_model_uses_dropout_and_stays_finite():
 # ---------------------------------------------------------------------------------------------
 # CUDA-graph front ends
 # ---------------------------------------------------------------------------------------------
-def test_graphed_hot_path_equals_eager():
+@pytest.mark.parametrize("sm_split", [None, (100, 40)])
+def test_graphed_hot_path_equals_eager(sm_split):
+    """sm_split: the persistent SFormer kernel on its own share of the SMs next to the TFormer / head chain (avf_set_sm_cap);
+    results must not depend on the partition, and the cap must be restored afterwards."""
     T, B, seed = 16, 9, 61
     m = _model(seed, T, "bf16").eval()
     stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
     dev = (stage3.bfloat16().cuda(), frame.bfloat16().cuda(), audio.cuda())
     with torch.no_grad():
-        g = A.GraphedHotPath(m, *dev)
+        g = A.GraphedHotPath(m, *dev, sm_split=sm_split)
+        assert A._lib.lib().avf_set_sm_cap(0) == 0
         for it in range(3):
             s3, fr, au = O.synth_hot_path_inputs(seed + it, B, T)
             dev = (s3.bfloat16().cuda(), fr.bfloat16().cuda(), au.cuda())
