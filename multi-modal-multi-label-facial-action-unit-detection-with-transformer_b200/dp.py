@@ -45,3 +45,42 @@ def allreduce_mean_(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
         flat_grad.div_(dist.get_world_size(group))
     return flat_grad
+
+
+class PipelinedLogitGather:
+    """Evaluation logit gather that does not stall the next batch: submit(out21) copies the rank's [b, 21] logits into one of
+    two staging buffers and starts the all-gather asynchronously (NCCL runs it on its own stream, ordered behind the copy);
+    the gathered [world*b, 21] tensor of a submit is valid after wait() or after the submit two calls later.  The transformer
+    hot path of batch i+1 thus overlaps the collective of batch i — clips are independent, nothing in the compute waits for
+    the gather.  With one rank it degenerates to returning the input."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.stage = [None, None]
+        self.out = [None, None]
+        self.work = [None, None]
+        self.k = 0
+
+    def submit(self, out21: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return out21
+        i = self.k & 1
+        self.k += 1
+        if self.work[i] is not None:
+            self.work[i].wait()                       # the gather that last used this pair of buffers (two submits ago)
+        if self.stage[i] is None or self.stage[i].shape != out21.shape:
+            self.stage[i] = torch.empty_like(out21)
+            self.out[i] = torch.empty((self.world * out21.shape[0],) + tuple(out21.shape[1:]), dtype=out21.dtype, device=out21.device)
+        self.stage[i].copy_(out21, non_blocking=True)
+        if out21.is_cuda:
+            self.work[i] = dist.all_gather_into_tensor(self.out[i], self.stage[i], group=self.group, async_op=True)
+        else:
+            self.work[i] = dist.all_gather(list(self.out[i].chunk(self.world)), self.stage[i], group=self.group, async_op=True)
+        return self.out[i]
+
+    def wait(self) -> None:
+        for i in (0, 1):
+            if self.work[i] is not None:
+                self.work[i].wait()
+                self.work[i] = None

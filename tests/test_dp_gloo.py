@@ -46,6 +46,18 @@ def _worker(rank, world, port, out_dir):
         bucket = torch.arange(10, dtype=torch.float32) * (rank + 1)
         A.dp.allreduce_mean_(bucket)
         assert torch.allclose(bucket, torch.arange(10, dtype=torch.float32) * 1.5)
+        # pipelined gather (bench.py at N > 1): three batches in flight over two buffer pairs, results valid after wait() / two submits
+        pipe = A.dp.PipelinedLogitGather()
+        outs = []
+        for step in range(3):
+            mine = torch.full((4, 21), float(10 * step + rank))
+            outs.append((step, pipe.submit(mine)))
+            if step == 2:                                               # buffer pair 0 is being reused: its first result was waited for
+                pass
+        pipe.wait()
+        for step, got in outs[1:]:                                      # (outs[0] shares its buffers with step 2)
+            for r in range(world):
+                assert torch.equal(got[4 * r: 4 * r + 4], torch.full((4, 21), float(10 * step + r)))
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()
