@@ -37,7 +37,8 @@ struct GemmCfg {
   static constexpr int W_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+  static constexpr int BIAS_OFF = BAR_OFF + 256;            // [2][BN] fp32: the tile's slice of the bias vector, staged per accumulator buffer
+  static constexpr int SMEM_BYTES = BIAS_OFF + 2 * BN * 4 + 1024;   // barriers + bias slices + slack for 1024B alignment
   static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator; power of two >= 32
 };
 
@@ -66,7 +67,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
   if (flags & AVF_EPI_BIAS) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+      const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j);     // shared memory (staged per tile by the epilogue warps)
       f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
     }
   }
@@ -242,6 +243,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t buf = lt & 1, aph = (lt >> 1) & 1;
       const int row = m0 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * BN + half * HALF_COLS;
+      // The tile's bias slice goes to shared memory BEFORE the wait for the accumulator (one global load per thread, hidden
+      // behind the main loop) instead of eight dependent L2 round trips per 32-column chunk inside the epilogue.  Two slices
+      // (one per accumulator buffer) and the barrier below make the reuse safe: a warp reaches tile t+2 only after every
+      // epilogue warp has passed the barrier of tile t+1, i.e. finished reading the slice of tile t.
+      const float* bias_t = bias;
+      if (flags & AVF_EPI_BIAS) {
+        float* bs = reinterpret_cast<float*>(smem + Cfg::BIAS_OFF) + buf * BN;
+        for (int i = threadIdx.x - 128; i < BN; i += 256) bs[i] = __ldg(bias + n0 + i);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bias_t = bs - n0;
+      }
       if constexpr (HALF_COLS <= 64) {
         // Narrow tiles are epilogue-latency bound (K is short on this path): request the thread's residual fragment BEFORE
         // waiting for the accumulator, so that the HBM/L2 round trip overlaps the main loop of this tile.
@@ -265,7 +277,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
           if (row < M)
-            epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N, want_res ? &pre[c0 / 4] : nullptr);
+            epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N, want_res ? &pre[c0 / 4] : nullptr);
         }
       } else {
         mbar_wait(&acc_full[buf], aph);
@@ -280,7 +292,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
-          if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias, res, ld_res, flags, aux, ld_aux, drop, N);
+          if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N);
         }
       }
     }
