@@ -89,6 +89,10 @@ int         avf_encoder_fused_supported(const avf_stack_shape* s, int mode);
  * Returns the previous value.  Lets a caller run two kernel chains side by side on disjoint SM sets (each persistent CTA
  * owns a whole SM): e.g. cap 116 around the SFormer launch, cap 32 around the TFormer / head chain on another stream. */
 int         avf_set_sm_cap(int cap);
+/* Programmatic dependent launch of every kernel of the library (default on): a kernel is scheduled while its predecessor in
+ * the stream still runs and waits (griddepcontrol.wait) for it to complete before it touches memory.  0 = plain launches
+ * (A/B tests).  Returns the previous setting. */
+int         avf_set_pdl_enabled(int enabled);
 /* Developer aid: 64 per-phase cycle counters of the fused kernel when the library is built with -DAVF_FUSED_PROF
  * (tools/fused_phases.py); AVF_EUNSUPPORTED otherwise. */
 int         avf_debug_fused_prof(uint64_t* out64, int reset);

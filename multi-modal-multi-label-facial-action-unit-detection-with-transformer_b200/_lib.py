@@ -94,6 +94,7 @@ SIGNATURES = {
                                              ctypes.POINTER(LayerGrads), ctypes.c_int, _c_p, _sz, ctypes.c_float, ctypes.c_uint64, _c_p, _c_p]),
     "avf_dropout_mask": (ctypes.c_int, [ctypes.c_float, ctypes.c_uint64, _c_p, _i32, _i32, _i32, _i32, _c_p, _c_p]),
     "avf_set_sm_cap": (ctypes.c_int, [ctypes.c_int]),
+    "avf_set_pdl_enabled": (ctypes.c_int, [ctypes.c_int]),
     "avf_debug_set_trap_buffer": (ctypes.c_int, [_c_p]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
@@ -166,6 +167,8 @@ def lib() -> ctypes.CDLL:
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(handle, name)       # AttributeError here = header/library mismatch: fail loudly
                 fn.restype, fn.argtypes = res, args
+            if os.environ.get("AVF_PDL", "") in ("0", "off"):
+                handle.avf_set_pdl_enabled(0)
             if handle.avf_abi_version() != 1:
                 raise RuntimeError("avformer_b200: ABI version mismatch")
             _lib = handle

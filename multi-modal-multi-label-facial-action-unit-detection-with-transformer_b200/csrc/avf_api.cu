@@ -12,6 +12,8 @@ namespace avf {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_pdl{1};        // avf_set_pdl_enabled
+bool pdl_enabled() { return g_pdl.load() != 0; }
 static std::atomic<int> g_sm_cap{0};     // avf_set_sm_cap
 int sm_cap() { return g_sm_cap.load(); }
 static std::atomic<int> g_fused{1};      // avf_set_fused_enabled: 0 forces the kernel-per-op path (A/B tests)
@@ -150,6 +152,8 @@ int avf_set_fused_enabled(int enabled) {
   const int old = g_fused.exchange(enabled ? 1 : 0);
   return old;
 }
+
+int avf_set_pdl_enabled(int enabled) { return g_pdl.exchange(enabled ? 1 : 0); }
 
 int avf_set_sm_cap(int cap) { return g_sm_cap.exchange(cap > 0 ? cap : 0); }
 

@@ -27,6 +27,8 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
 template <int DH, int NP>    // NP = tokens padded to a multiple of 16 (16 / 32 / 48 / 64)
 __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                             int n_problems, int n_tok, int heads, float scale_log2e, int q_rows) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   // q_rows: only the first q_rows query rows of every sequence are computed and written (compactly: out [n_seq * q_rows, inner]);
   // q_rows = n_tok is plain self-attention, q_rows = 1 is the TFormer's last layer, of which only the cls row is consumed.
   constexpr int PITCH = DH + 8;                       // elements; (DH*2+16) bytes keeps 8 consecutive rows on distinct banks
@@ -148,7 +150,7 @@ int launch(const void* qkv, void* out, int n_seq, int n_tok, int heads, int q_ro
   const int n_problems = n_seq * heads;
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(DH));
   constexpr int kWarps = DH == 32 ? 4 : 2;
-  attention_mma_kernel<DH, NP><<<ceil_div(n_problems, kWarps), kWarps * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+  launch_pdl(attention_mma_kernel<DH, NP>, ceil_div(n_problems, kWarps), kWarps * 32, 0, st, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
                                                                       n_problems, n_tok, heads, scale_log2e, q_rows);
   AVF_LAUNCH_CHECK("attention_mma_kernel");
   return 0;
@@ -175,6 +177,8 @@ __global__ void __launch_bounds__(BwdCfg<DH, NP>::WARPS * 32) attention_bwd_mma_
                                                                                        const __nv_bfloat16* __restrict__ dout,
                                                                                        __nv_bfloat16* __restrict__ dqkv, int n_problems,
                                                                                        int n_tok, int heads, float scale) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   using Cfg = BwdCfg<DH, NP>;
   constexpr int PITCH = Cfg::PITCH, WARPS = Cfg::WARPS;
   __shared__ __align__(16) __nv_bfloat16 smem[WARPS][4][NP][PITCH];
@@ -372,8 +376,7 @@ template <int DH, int NP>
 int launch_bwd(const void* qkv, const void* dout, void* dqkv, int n_seq, int n_tok, int heads, cudaStream_t st) {
   const int n_problems = n_seq * heads;
   constexpr int kWarps = BwdCfg<DH, NP>::WARPS;
-  attention_bwd_mma_kernel<DH, NP><<<ceil_div(n_problems, kWarps), kWarps * 32, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqkv), n_problems, n_tok, heads,
+  launch_pdl(attention_bwd_mma_kernel<DH, NP>, ceil_div(n_problems, kWarps), kWarps * 32, 0, st, static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqkv), n_problems, n_tok, heads,
       1.0f / sqrtf(float(DH)));
   AVF_LAUNCH_CHECK("attention_bwd_mma_kernel");
   return 0;

@@ -43,6 +43,34 @@ int sm_cap();          // avf_set_sm_cap: upper bound on the grid of the persist
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization
+// attribute and starts with pdl_wait() (griddepcontrol.wait: blocks until the preceding grid of the stream has completed and
+// its writes are visible) followed by pdl_trigger() (lets the NEXT kernel of the stream be scheduled while this one runs; it
+// blocks in its own pdl_wait()).  The launch latency and the prologue of a kernel (barrier set-up, TMEM allocation, tensor-map
+// prefetch) thus overlap the tail of its predecessor — the hot path is a chain of 60 (forward) / 330 (training step) mostly
+// short launches.  Captured CUDA graphs keep the programmatic edges.  avf_set_pdl_enabled(0) launches everything plainly.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // numeric helpers
 // ---------------------------------------------------------------------------------------------
 // models/heads.py:164-166.  kFast uses MUFU.TANH (rel. error 2^-11, below bf16 resolution).

@@ -164,6 +164,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // the prologue above overlapped the previous kernel; its results are needed from here on
+  pdl_trigger();
 
   // Warps 0 and 1 run their loops with all 32 lanes on warp-uniform values (addresses, descriptors and loop state then live in
   // uniform registers and the issue loops are a few instructions per TMA / MMA); only the elected lane issues.
@@ -374,7 +376,7 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
   }
   const int n_tiles = (n / BN) * ceil_div(m, BM) * splits;
   const int cap = sm_cap();
-  kern<<<min(n_tiles, cap > 0 ? min(cap, sm_count()) : sm_count()), 384, Cfg::SMEM_BYTES, stream>>>(ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
+  launch_pdl(kern, min(n_tiles, cap > 0 ? min(cap, sm_count()) : sm_count()), 384, Cfg::SMEM_BYTES, stream, ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,
                                                                    static_cast<__nv_bfloat16*>(const_cast<void*>(aux)), ld_aux, splits, split_stride, drop);
   AVF_LAUNCH_CHECK("gemm_umma_kernel");
   return 0;
@@ -383,6 +385,8 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
 namespace {
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t n, float* __restrict__ out,
                                                             int accumulate) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = *reinterpret_cast<const float4*>(part + i);
@@ -439,7 +443,7 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
                       : launch_gemm<64, 8, float, true, true>(a, lda, w, ldw, part, ldc, nullptr, nullptr, 0, m, n, k, 0, nullptr, 0, splits, stride, stream);
     if (e) return e;
     if (splits > 1 || accumulate) {
-      splitk_reduce_kernel<<<unsigned((elems / 4 + 255) / 256), 256, 0, stream>>>(part, splits, elems, out, accumulate ? 1 : 0);
+      launch_pdl(splitk_reduce_kernel, unsigned((elems / 4 + 255) / 256), 256, 0, stream, part, splits, elems, out, accumulate ? 1 : 0);
       AVF_LAUNCH_CHECK("splitk_reduce_kernel");
     }
     return 0;

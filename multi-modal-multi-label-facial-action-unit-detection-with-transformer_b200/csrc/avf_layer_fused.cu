@@ -1032,6 +1032,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();        // the prologue above overlapped the previous kernel; its results are needed from here on
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) producer_main<IO>(a, smem, bars);
@@ -1050,6 +1052,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
 
 // pos [n_tok, 256] -> pos_t [256 / 4][POS_LD][4] (one tiny launch in front of the fused kernel; 64 KB)
 __global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restrict__ pos, float* __restrict__ pos_t, int n_tok) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int c = blockIdx.x * 4 + (threadIdx.x & 3), t = threadIdx.x >> 2;
   pos_t[(blockIdx.x * POS_LD + t) * 4 + (threadIdx.x & 3)] = t < n_tok ? pos[t * DIM + c] : 0.f;
 }
@@ -1105,7 +1109,7 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
   static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
   a.in = in; a.out = out; a.pos = pos; a.pos_t = static_cast<const float*>(scratch); a.ld_in = ld_in; a.ld_out = ld_out;
   if (io_kind == IO_NCHW_BF16) {
-    pos_transpose_kernel<<<DIM / 4, 256, 0, st>>>(pos, static_cast<float*>(scratch), s->n_tok);
+    launch_pdl(pos_transpose_kernel, DIM / 4, 256, 0, st, pos, static_cast<float*>(scratch), s->n_tok);
     AVF_LAUNCH_CHECK("pos_transpose_kernel");
   }
   a.n_seq = s->n_seq; a.n_tok = s->n_tok;
@@ -1134,9 +1138,9 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
   const int cap = sm_cap();
   const int grid = min(a.n_tiles, cap > 0 ? min(cap, sm_count_cached()) : sm_count_cached());
   if (io_kind == IO_NCHW_BF16)
-    encoder_fused_kernel<IO_NCHW_BF16><<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(a);
+    launch_pdl(encoder_fused_kernel<IO_NCHW_BF16>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
   else
-    encoder_fused_kernel<IO_ROWS_F32><<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(a);
+    launch_pdl(encoder_fused_kernel<IO_ROWS_F32>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
   AVF_LAUNCH_CHECK("encoder_fused_kernel");
   return 0;
 }

@@ -16,6 +16,8 @@ namespace {
 template <typename OutT, int VEC>   // VEC float4 per lane: dim = 128 * VEC
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, OutT* __restrict__ y, int rows) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   constexpr int DIM = 128 * VEC;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -59,6 +61,8 @@ template <typename OutT>
 __global__ void bn_rows_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ g, const float* __restrict__ b,
                                const float* __restrict__ mean, const float* __restrict__ var, OutT* __restrict__ y,
                                int rows, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * dim) return;
   const int r = idx / dim, c = idx - r * dim;
@@ -101,6 +105,8 @@ template <> struct Vec16<float> {
 template <typename InT>
 __global__ void __launch_bounds__(256) sformer_pack_kernel(const InT* __restrict__ fmap, const float* __restrict__ pos,
                                                            float* __restrict__ x, int n_frames, int dim, int hw) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   extern __shared__ float tile[];               // [dim][pitch], pitch = hw | 1
   constexpr int V = Vec16<InT>::N;
   const int pitch = hw | 1, n = dim * hw;
@@ -137,6 +143,8 @@ __global__ void __launch_bounds__(256) sformer_pack_kernel(const InT* __restrict
 // x [F*hw, dim] -> fmap [F, dim, hw]   (models/vformer.py:257-259)
 template <typename OutT>
 __global__ void __launch_bounds__(256) sformer_unpack_kernel(const float* __restrict__ x, OutT* __restrict__ fmap, int n_frames, int dim, int hw) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   extern __shared__ float tile[];               // [dim][pitch]
   constexpr int V = Vec16<OutT>::N;
   const int pitch = hw | 1, n = dim * hw;
@@ -173,6 +181,8 @@ __global__ void __launch_bounds__(256) sformer_unpack_kernel(const float* __rest
 template <typename InT>
 __global__ void tformer_embed_kernel(const InT* __restrict__ frames, const float* __restrict__ cls, const float* __restrict__ pos,
                                      float* __restrict__ x, int n_clips, int T, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;      // over float4 groups
   const int d4 = dim >> 2;
   const size_t total = size_t(n_clips) * (T + 1) * d4;
@@ -193,6 +203,8 @@ __global__ void tformer_embed_kernel(const InT* __restrict__ frames, const float
 }
 
 __global__ void rows_gather_kernel(const float* __restrict__ x, size_t src_row_stride, float* __restrict__ y, int rows, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * dim) return;
   const int r = idx / dim, c = idx - r * dim;
@@ -200,6 +212,8 @@ __global__ void rows_gather_kernel(const float* __restrict__ x, size_t src_row_s
 }
 
 __global__ void add_row_periodic_kernel(float* __restrict__ x, int ld_x, const float* __restrict__ pos, int rows, int dim, int period) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * dim) return;
   const int r = idx / dim, c = idx - r * dim;
@@ -207,6 +221,8 @@ __global__ void add_row_periodic_kernel(float* __restrict__ x, int ld_x, const f
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(s + i);
@@ -219,6 +235,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16*
   }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, size_t n) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __bfloat162float(s[i]);
 }
@@ -230,6 +248,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) au_logits_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ w_last,
                                                         float* __restrict__ out21, int* __restrict__ decisions, int n_clips, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= n_clips * 12) return;
@@ -257,6 +277,8 @@ __global__ void __launch_bounds__(256) au_logits_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) au_bce_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ labels,
                                                      const float* __restrict__ pw, float* __restrict__ loss_out,
                                                      float* __restrict__ dlogits, int n_clips) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float red[2][8];
   __shared__ float tot[2];
   float lsum = 0.f, nvalid = 0.f;
@@ -300,6 +322,8 @@ __global__ void __launch_bounds__(256) au_bce_kernel(const float* __restrict__ l
 __global__ void __launch_bounds__(256) au_confusion_kernel(const float* __restrict__ pred, int ld_pred, float thresh,
                                                            const float* __restrict__ labels, int ld_lab, float ignore,
                                                            unsigned long long* __restrict__ counts, int n_rows) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ unsigned int sc[12][4];
   if (threadIdx.x < 48) sc[threadIdx.x / 4][threadIdx.x % 4] = 0;
   __syncthreads();
@@ -327,8 +351,8 @@ int layernorm(int out_mode, const float* x, int ld_x, const float* g, const floa
   dim3 grid(ceil_div(rows, wpb)), block(wpb * 32);
 #define AVF_LN(V)                                                                                                   \
   case V:                                                                                                           \
-    if (out_mode == AVF_BF16) layernorm_kernel<__nv_bfloat16, V><<<grid, block, 0, st>>>(x, ld_x, g, b, static_cast<__nv_bfloat16*>(y), rows); \
-    else layernorm_kernel<float, V><<<grid, block, 0, st>>>(x, ld_x, g, b, static_cast<float*>(y), rows);             \
+    if (out_mode == AVF_BF16) launch_pdl(layernorm_kernel<__nv_bfloat16, V>, grid, block, 0, st, x, ld_x, g, b, static_cast<__nv_bfloat16*>(y), rows); \
+    else launch_pdl(layernorm_kernel<float, V>, grid, block, 0, st, x, ld_x, g, b, static_cast<float*>(y), rows);             \
     break;
   switch (dim / 128) {
     AVF_LN(1) AVF_LN(2) AVF_LN(3) AVF_LN(4) AVF_LN(5) AVF_LN(6) AVF_LN(7) AVF_LN(8)
@@ -341,8 +365,8 @@ int layernorm(int out_mode, const float* x, int ld_x, const float* g, const floa
 int bn_rows(int out_mode, const float* x, int ld_x, const float* g, const float* b, const float* mean, const float* var, void* y,
             int rows, int dim, cudaStream_t st) {
   const int n = rows * dim;
-  if (out_mode == AVF_BF16) bn_rows_kernel<__nv_bfloat16><<<ceil_div(n, 256), 256, 0, st>>>(x, ld_x, g, b, mean, var, static_cast<__nv_bfloat16*>(y), rows, dim);
-  else bn_rows_kernel<float><<<ceil_div(n, 256), 256, 0, st>>>(x, ld_x, g, b, mean, var, static_cast<float*>(y), rows, dim);
+  if (out_mode == AVF_BF16) launch_pdl(bn_rows_kernel<__nv_bfloat16>, ceil_div(n, 256), 256, 0, st, x, ld_x, g, b, mean, var, static_cast<__nv_bfloat16*>(y), rows, dim);
+  else launch_pdl(bn_rows_kernel<float>, ceil_div(n, 256), 256, 0, st, x, ld_x, g, b, mean, var, static_cast<float*>(y), rows, dim);
   AVF_LAUNCH_CHECK("bn_rows_kernel");
   return 0;
 }
@@ -367,8 +391,8 @@ int sformer_pack(int io_mode, const void* fmap, const float* pos, float* x, int 
     cfg = true;
   }
   const int grid = sformer_grid(n_frames, smem);
-  if (io_mode == AVF_BF16) sformer_pack_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(fmap), pos, x, n_frames, dim, hw);
-  else sformer_pack_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float*>(fmap), pos, x, n_frames, dim, hw);
+  if (io_mode == AVF_BF16) launch_pdl(sformer_pack_kernel<__nv_bfloat16>, grid, 256, smem, st, static_cast<const __nv_bfloat16*>(fmap), pos, x, n_frames, dim, hw);
+  else launch_pdl(sformer_pack_kernel<float>, grid, 256, smem, st, static_cast<const float*>(fmap), pos, x, n_frames, dim, hw);
   AVF_LAUNCH_CHECK("sformer_pack_kernel");
   return 0;
 }
@@ -386,8 +410,8 @@ int sformer_unpack(int io_mode, const float* x, void* fmap, int n_frames, int di
     cfg = true;
   }
   const int grid = sformer_grid(n_frames, smem);
-  if (io_mode == AVF_BF16) sformer_unpack_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, static_cast<__nv_bfloat16*>(fmap), n_frames, dim, hw);
-  else sformer_unpack_kernel<float><<<grid, 256, smem, st>>>(x, static_cast<float*>(fmap), n_frames, dim, hw);
+  if (io_mode == AVF_BF16) launch_pdl(sformer_unpack_kernel<__nv_bfloat16>, grid, 256, smem, st, x, static_cast<__nv_bfloat16*>(fmap), n_frames, dim, hw);
+  else launch_pdl(sformer_unpack_kernel<float>, grid, 256, smem, st, x, static_cast<float*>(fmap), n_frames, dim, hw);
   AVF_LAUNCH_CHECK("sformer_unpack_kernel");
   return 0;
 }
@@ -396,22 +420,22 @@ int tformer_embed(int io_mode, const void* frames, const float* cls, const float
   AVF_REQUIRE(n_clips > 0 && T > 0 && dim % 4 == 0, AVF_EINVAL, "tformer_embed: n_clips=%d T=%d dim=%d", n_clips, T, dim);
   const size_t total = size_t(n_clips) * (T + 1) * (dim / 4);
   const unsigned grid = unsigned((total + 255) / 256);
-  if (io_mode == AVF_BF16) tformer_embed_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(frames), cls, pos, x, n_clips, T, dim);
-  else tformer_embed_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(frames), cls, pos, x, n_clips, T, dim);
+  if (io_mode == AVF_BF16) launch_pdl(tformer_embed_kernel<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(frames), cls, pos, x, n_clips, T, dim);
+  else launch_pdl(tformer_embed_kernel<float>, grid, 256, 0, st, static_cast<const float*>(frames), cls, pos, x, n_clips, T, dim);
   AVF_LAUNCH_CHECK("tformer_embed_kernel");
   return 0;
 }
 
 int rows_gather(const float* x, size_t src_row_stride, float* y, int rows, int dim, cudaStream_t st) {
   AVF_REQUIRE(rows > 0 && dim > 0, AVF_EINVAL, "cls_extract: empty input");
-  rows_gather_kernel<<<ceil_div(rows * dim, 256), 256, 0, st>>>(x, src_row_stride, y, rows, dim);
+  launch_pdl(rows_gather_kernel, ceil_div(rows * dim, 256), 256, 0, st, x, src_row_stride, y, rows, dim);
   AVF_LAUNCH_CHECK("rows_gather_kernel");
   return 0;
 }
 
 int add_row_periodic(float* x, int ld_x, const float* pos, int rows, int dim, int period, cudaStream_t st) {
   AVF_REQUIRE(rows > 0 && dim > 0 && period > 0, AVF_EINVAL, "add_row_periodic: empty input");
-  add_row_periodic_kernel<<<ceil_div(rows * dim, 256), 256, 0, st>>>(x, ld_x, pos, rows, dim, period);
+  launch_pdl(add_row_periodic_kernel, ceil_div(rows * dim, 256), 256, 0, st, x, ld_x, pos, rows, dim, period);
   AVF_LAUNCH_CHECK("add_row_periodic_kernel");
   return 0;
 }
@@ -419,20 +443,20 @@ int add_row_periodic(float* x, int ld_x, const float* pos, int rows, int dim, in
 int cast_f32_bf16(const float* s, void* d, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
   AVF_REQUIRE((reinterpret_cast<uintptr_t>(s) & 15) == 0 && (reinterpret_cast<uintptr_t>(d) & 7) == 0, AVF_EINVAL, "cast: unaligned pointers");
-  cast_f32_bf16_kernel<<<unsigned((n / 4 + 256) / 256), 256, 0, st>>>(s, static_cast<__nv_bfloat16*>(d), n);
+  launch_pdl(cast_f32_bf16_kernel, unsigned((n / 4 + 256) / 256), 256, 0, st, s, static_cast<__nv_bfloat16*>(d), n);
   AVF_LAUNCH_CHECK("cast_f32_bf16_kernel");
   return 0;
 }
 int cast_bf16_f32(const void* s, float* d, size_t n, cudaStream_t st) {
   if (n == 0) return 0;
-  cast_bf16_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(s), d, n);
+  launch_pdl(cast_bf16_f32_kernel, unsigned((n + 255) / 256), 256, 0, st, static_cast<const __nv_bfloat16*>(s), d, n);
   AVF_LAUNCH_CHECK("cast_bf16_f32_kernel");
   return 0;
 }
 
 int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* decisions, int n_clips, int dim, cudaStream_t st) {
   AVF_REQUIRE(n_clips > 0 && dim % 4 == 0 && ld_x % 4 == 0, AVF_EINVAL, "au_logits: n_clips=%d dim=%d", n_clips, dim);
-  au_logits_kernel<<<ceil_div(n_clips * 12, 8), 256, 0, st>>>(x, ld_x, w_last, out21, decisions, n_clips, dim);
+  launch_pdl(au_logits_kernel, ceil_div(n_clips * 12, 8), 256, 0, st, x, ld_x, w_last, out21, decisions, n_clips, dim);
   AVF_LAUNCH_CHECK("au_logits_kernel");
   return 0;
 }
@@ -440,14 +464,14 @@ int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* 
 int au_confusion(const float* pred, int ld_pred, float thresh, const float* labels, int ld_lab, float ignore, unsigned long long* counts, int n_rows,
                  cudaStream_t st) {
   AVF_REQUIRE(n_rows > 0 && pred && labels && counts, AVF_EINVAL, "au_confusion_update: n_rows=%d", n_rows);
-  au_confusion_kernel<<<std::min(ceil_div(n_rows * 12, 256), 296), 256, 0, st>>>(pred, ld_pred, thresh, labels, ld_lab, ignore, counts, n_rows);
+  launch_pdl(au_confusion_kernel, std::min(ceil_div(n_rows * 12, 256), 296), 256, 0, st, pred, ld_pred, thresh, labels, ld_lab, ignore, counts, n_rows);
   AVF_LAUNCH_CHECK("au_confusion_kernel");
   return 0;
 }
 
 int au_bce(const float* logits, int ld, const float* labels, const float* pw, float* loss_out, float* dlogits, int n_clips, cudaStream_t st) {
   AVF_REQUIRE(n_clips > 0, AVF_EINVAL, "au_bce_loss: n_clips=%d", n_clips);
-  au_bce_kernel<<<1, 256, 0, st>>>(logits, ld, labels, pw, loss_out, dlogits, n_clips);
+  launch_pdl(au_bce_kernel, 1, 256, 0, st, logits, ld, labels, pw, loss_out, dlogits, n_clips);
   AVF_LAUNCH_CHECK("au_bce_kernel");
   return 0;
 }

@@ -15,6 +15,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
                                                        OutT* __restrict__ C, int ldc, const float* __restrict__ bias,
                                                        const float* __restrict__ res, int ld_res, int M, int N, int K, int flags) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float As[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256) gemm_f32_generic_kernel(const float* __re
                                                                long w_rs, long w_cs, OutT* __restrict__ C, int ldc,
                                                                const float* __restrict__ bias, const float* __restrict__ res, int ld_res,
                                                                float* aux, int ld_aux, int M, int N, int K, int flags, DropSpec drop) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float As[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -163,6 +167,8 @@ __device__ __forceinline__ void store_frag(T* __restrict__ p, const float (&src)
 template <typename T, int DH>
 __global__ void __launch_bounds__(DH == 32 ? 512 : 256) attention_small_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n_seq, int n_tok,
                                                               int heads, int spb, int hpb, float scale_log2e) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   extern __shared__ uint8_t smem_attn[];
   T* kv = reinterpret_cast<T*>(smem_attn);                // [spb][n_tok][2][hpb*DH]  (k | v of the block's head group)
   const int inner = heads * DH;
@@ -229,8 +235,8 @@ int linear_f32(const float* a, int lda, const float* w, const float* bias, const
   AVF_REQUIRE(m > 0 && n > 0 && k > 0, AVF_EINVAL, "linear: empty problem m=%d n=%d k=%d", m, n, k);
   AVF_REQUIRE(k % 16 == 0 && lda % 4 == 0, AVF_EUNSUPPORTED, "linear(fp32): K=%d must be a multiple of 16 (lda=%d of 4)", k, lda);
   dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
-  if (c_mode == AVF_BF16) gemm_f32_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, lda, w, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags);
-  else gemm_f32_kernel<float><<<grid, 256, 0, st>>>(a, lda, w, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags);
+  if (c_mode == AVF_BF16) launch_pdl(gemm_f32_kernel<__nv_bfloat16>, grid, 256, 0, st, a, lda, w, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, m, n, k, flags);
+  else launch_pdl(gemm_f32_kernel<float>, grid, 256, 0, st, a, lda, w, static_cast<float*>(c), ldc, bias, res, ld_res, m, n, k, flags);
   AVF_LAUNCH_CHECK("gemm_f32_kernel");
   return 0;
 }
@@ -244,9 +250,9 @@ int gemm_f32(int trans_a, int trans_b, const float* a, int lda, const float* w, 
   dim3 grid(ceil_div(n, 64), ceil_div(m, 64));
   const long a_rs = trans_a ? 1 : lda, a_cs = trans_a ? lda : 1, w_rs = trans_b ? 1 : ldw, w_cs = trans_b ? ldw : 1;
   if (c_mode == AVF_BF16)
-    gemm_f32_generic_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
+    launch_pdl(gemm_f32_generic_kernel<__nv_bfloat16>, grid, 256, 0, st, a, a_rs, a_cs, w, w_rs, w_cs, static_cast<__nv_bfloat16*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
   else
-    gemm_f32_generic_kernel<float><<<grid, 256, 0, st>>>(a, a_rs, a_cs, w, w_rs, w_cs, static_cast<float*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
+    launch_pdl(gemm_f32_generic_kernel<float>, grid, 256, 0, st, a, a_rs, a_cs, w, w_rs, w_cs, static_cast<float*>(c), ldc, bias, res, ld_res, aux, ld_aux, m, n, k, flags, drop);
   AVF_LAUNCH_CHECK("gemm_f32_generic_kernel");
   return 0;
 }
@@ -271,7 +277,7 @@ static int launch_attention(const void* qkv, void* out, int n_seq, int n_tok, in
     cfg = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(DH));
-  kern<<<dim3(ceil_div(n_seq, spb), ceil_div(heads, hpb)), threads, smem, st>>>(static_cast<const T*>(qkv), static_cast<T*>(out), n_seq, n_tok, heads, spb, hpb,
+  launch_pdl(kern, dim3(ceil_div(n_seq, spb), ceil_div(heads, hpb)), threads, smem, st, static_cast<const T*>(qkv), static_cast<T*>(out), n_seq, n_tok, heads, spb, hpb,
                                                                                scale_log2e);
   AVF_LAUNCH_CHECK("attention_small_kernel");
   return 0;

@@ -42,6 +42,8 @@ template <> struct RowVec<float> {
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __restrict__ x, size_t ld, int rows, int cols, int rows_per_chunk,
                                                                  float* __restrict__ part) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   constexpr int N = RowVec<T>::N;
   __shared__ float red[8][32 * N + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const T* __rest
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, size_t ld, int rows, int cols, int rows_per_chunk,
                                                              float* __restrict__ part) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -96,6 +100,8 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
 // loads overlap; the order of the additions is fixed.
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, int n_out,
                                                            float* o0, float* o1, float* o2, float beta) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + tx, width = cols * n_out;
@@ -138,6 +144,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dyn, float* dres, int ld_d,
                                                             void* __restrict__ dxb, int dxb_bf16, float* __restrict__ part, int rows,
                                                             int rows_per_block, DropSpec drop_in, DropSpec drop_out) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   constexpr int DIM = 128 * VEC;
   __shared__ float red[8][DIM];
   drop_in = drop_resolve(drop_in);
@@ -240,11 +248,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) masked_copy_kernel(const float* __restrict__ x, OutT* __restrict__ y, size_t n, DropSpec drop) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   drop = drop_resolve(drop);
   if (i < n) y[i] = from_f32<OutT>(x[i] * drop_factor(drop, uint32_t(i)));
 }
 __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ out, size_t n, DropSpec drop) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   drop = drop_resolve(drop);
   if (i < n) out[i] = drop_factor(drop, uint32_t(i));
@@ -258,6 +270,8 @@ __global__ void __launch_bounds__(256) dropout_mask_kernel(float* __restrict__ o
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) attention_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, T* __restrict__ dqkv,
                                                             int n_tok, int heads, float scale) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   extern __shared__ float sm[];
   constexpr int P = DH + 1;
   const int N = n_tok, NP = N + 1;
@@ -334,6 +348,8 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const T* __restrict_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) au_logits_bwd_dx_kernel(const float* __restrict__ dl, int ld_dl, const float* __restrict__ w_last,
                                                                float* __restrict__ dx, int ld_dx, int n_clips, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= size_t(n_clips) * 12 * dim) return;
   const int c = int(idx % dim);
@@ -343,6 +359,8 @@ __global__ void __launch_bounds__(256) au_logits_bwd_dx_kernel(const float* __re
 }
 __global__ void __launch_bounds__(256) au_logits_bwd_dw_kernel(const float* __restrict__ dl, int ld_dl, const float* __restrict__ x, int ld_x,
                                                                float* __restrict__ dw, int n_clips, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const int au = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= dim) return;
   float a = 0.f;
@@ -358,6 +376,8 @@ __global__ void __launch_bounds__(256) bn_train_fwd_kernel(const float* __restri
                                                            const float* __restrict__ b, float* run_mean, float* run_var, float momentum,
                                                            OutT* __restrict__ y, float* __restrict__ save_mean, float* __restrict__ save_rstd,
                                                            int rows, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float red[8][33];
   __shared__ float stat[2][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -403,6 +423,8 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ x
                                                      const float* __restrict__ g, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd_or_var, int batch_stats, float* __restrict__ dx,
                                                      int ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int dim) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   __shared__ float red[2][8][33];
   __shared__ float tot[2][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -448,6 +470,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float b1,
                                                    float b2, float eps, float wd, float inv_bc1, float inv_sqrt_bc2, int decoupled,
                                                    float grad_scale) {
+  pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
+  pdl_trigger();
   const size_t i = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float pv[4], gv[4], mv[4], vv[4];
@@ -517,14 +541,14 @@ int colsum(int in_mode, const void* x, size_t ld, int rows, int cols, float* out
   dim3 grid(col_blocks, ceil_div(rows, rpc));
   float* part = static_cast<float*>(ws);
   if (vectorised) {
-    if (in_mode == AVF_BF16) colsum_partial_vec_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
-    else colsum_partial_vec_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
+    if (in_mode == AVF_BF16) launch_pdl(colsum_partial_vec_kernel<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
+    else launch_pdl(colsum_partial_vec_kernel<float>, grid, 256, 0, st, static_cast<const float*>(x), ld, rows, cols, rpc, part);
   } else {
-    if (in_mode == AVF_BF16) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
-    else colsum_partial_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ld, rows, cols, rpc, part);
+    if (in_mode == AVF_BF16) launch_pdl(colsum_partial_kernel<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(x), ld, rows, cols, rpc, part);
+    else launch_pdl(colsum_partial_kernel<float>, grid, 256, 0, st, static_cast<const float*>(x), ld, rows, cols, rpc, part);
   }
   AVF_LAUNCH_CHECK("colsum_partial_kernel");
-  colsum_final_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(part, int(grid.y), cols, 1, out, nullptr, nullptr, beta);
+  launch_pdl(colsum_final_kernel, ceil_div(cols, 32), 256, 0, st, part, int(grid.y), cols, 1, out, nullptr, nullptr, beta);
   AVF_LAUNCH_CHECK("colsum_final_kernel");
   return 0;
 }
@@ -545,14 +569,14 @@ int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn
   float* part = static_cast<float*>(ws);
   const int xb16 = dxb_mode == AVF_BF16 ? 1 : 0;
   switch (dim / 128) {
-    case 1: layernorm_bwd_kernel<1><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
-    case 2: layernorm_bwd_kernel<2><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
-    case 3: layernorm_bwd_kernel<3><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
-    default: layernorm_bwd_kernel<4><<<grid, 256, 0, st>>>(x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    case 1: launch_pdl(layernorm_bwd_kernel<1>, grid, 256, 0, st, x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    case 2: launch_pdl(layernorm_bwd_kernel<2>, grid, 256, 0, st, x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    case 3: launch_pdl(layernorm_bwd_kernel<3>, grid, 256, 0, st, x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
+    default: launch_pdl(layernorm_bwd_kernel<4>, grid, 256, 0, st, x, ld_x, gamma, dyn, dres, ld_d, dxb, xb16, part, rows, rpb, drop_in, drop_out); break;
   }
   AVF_LAUNCH_CHECK("layernorm_bwd_kernel");
   if (dgamma || dbeta || dbias) {
-    colsum_final_kernel<<<ceil_div(3 * dim, 32), 256, 0, st>>>(part, grid, dim, 3, dgamma, dbeta, dbias, beta_acc);
+    launch_pdl(colsum_final_kernel, ceil_div(3 * dim, 32), 256, 0, st, part, grid, dim, 3, dgamma, dbeta, dbias, beta_acc);
     AVF_LAUNCH_CHECK("colsum_final_kernel");
   }
   return 0;
@@ -561,8 +585,8 @@ int layernorm_bwd(const float* x, int ld_x, const float* gamma, const float* dyn
 int masked_copy(const float* x, void* y, int y_mode, int rows, int dim, DropSpec drop, cudaStream_t st) {
   const size_t n = size_t(rows) * dim;
   AVF_REQUIRE(n > 0 && n < (size_t(1) << 32), AVF_EINVAL, "masked_copy: %zu elements", n);
-  if (y_mode == AVF_BF16) masked_copy_kernel<__nv_bfloat16><<<unsigned((n + 255) / 256), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(y), n, drop);
-  else masked_copy_kernel<float><<<unsigned((n + 255) / 256), 256, 0, st>>>(x, static_cast<float*>(y), n, drop);
+  if (y_mode == AVF_BF16) launch_pdl(masked_copy_kernel<__nv_bfloat16>, unsigned((n + 255) / 256), 256, 0, st, x, static_cast<__nv_bfloat16*>(y), n, drop);
+  else launch_pdl(masked_copy_kernel<float>, unsigned((n + 255) / 256), 256, 0, st, x, static_cast<float*>(y), n, drop);
   AVF_LAUNCH_CHECK("masked_copy_kernel");
   return 0;
 }
@@ -570,7 +594,7 @@ int masked_copy(const float* x, void* y, int y_mode, int rows, int dim, DropSpec
 int dropout_mask(float* out, int rows, int cols, DropSpec drop, cudaStream_t st) {
   const size_t n = size_t(rows) * cols;
   AVF_REQUIRE(out && n > 0 && n < (size_t(1) << 32), AVF_EINVAL, "dropout_mask: %zu elements", n);
-  dropout_mask_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(out, n, drop);
+  launch_pdl(dropout_mask_kernel, unsigned((n + 255) / 256), 256, 0, st, out, n, drop);
   AVF_LAUNCH_CHECK("dropout_mask_kernel");
   return 0;
 }
@@ -585,7 +609,7 @@ static int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, i
     AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     cfg = true;
   }
-  kern<<<n_seq * heads, 128, smem, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(dout), static_cast<T*>(dqkv), n_tok, heads,
+  launch_pdl(kern, n_seq * heads, 128, smem, st, static_cast<const T*>(qkv), static_cast<const T*>(dout), static_cast<T*>(dqkv), n_tok, heads,
                                          rsqrtf(float(DH)));
   AVF_LAUNCH_CHECK("attention_bwd_kernel");
   return 0;
@@ -604,12 +628,12 @@ int au_logits_bwd(const float* dl, int ld_dl, const float* x, int ld_x, const fl
   AVF_REQUIRE(n_clips > 0 && dim > 0 && dl && w_last, AVF_EINVAL, "au_logits_bwd: n_clips=%d dim=%d", n_clips, dim);
   if (dx != nullptr) {
     const size_t total = size_t(n_clips) * 12 * dim;
-    au_logits_bwd_dx_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(dl, ld_dl, w_last, dx, ld_dx, n_clips, dim);
+    launch_pdl(au_logits_bwd_dx_kernel, unsigned((total + 255) / 256), 256, 0, st, dl, ld_dl, w_last, dx, ld_dx, n_clips, dim);
     AVF_LAUNCH_CHECK("au_logits_bwd_dx_kernel");
   }
   if (dw != nullptr) {
     AVF_REQUIRE(x != nullptr, AVF_EINVAL, "au_logits_bwd: dw needs the tokens");
-    au_logits_bwd_dw_kernel<<<dim3(ceil_div(dim, 256), 12), 256, 0, st>>>(dl, ld_dl, x, ld_x, dw, n_clips, dim);
+    launch_pdl(au_logits_bwd_dw_kernel, dim3(ceil_div(dim, 256), 12), 256, 0, st, dl, ld_dl, x, ld_x, dw, n_clips, dim);
     AVF_LAUNCH_CHECK("au_logits_bwd_dw_kernel");
   }
   return 0;
@@ -620,9 +644,9 @@ int bn_train_fwd(int out_mode, const float* x, int ld_x, const float* g, const f
   AVF_REQUIRE(rows > 1, AVF_EINVAL, "batch_norm(train): needs more than one row per channel (rows=%d)", rows);   // like torch
   AVF_REQUIRE(x && g && b && y && save_mean && save_rstd, AVF_EINVAL, "batch_norm(train): null pointer");
   if (out_mode == AVF_BF16)
-    bn_train_fwd_kernel<__nv_bfloat16><<<ceil_div(dim, 32), 256, 0, st>>>(x, ld_x, g, b, run_mean, run_var, momentum, static_cast<__nv_bfloat16*>(y), save_mean, save_rstd, rows, dim);
+    launch_pdl(bn_train_fwd_kernel<__nv_bfloat16>, ceil_div(dim, 32), 256, 0, st, x, ld_x, g, b, run_mean, run_var, momentum, static_cast<__nv_bfloat16*>(y), save_mean, save_rstd, rows, dim);
   else
-    bn_train_fwd_kernel<float><<<ceil_div(dim, 32), 256, 0, st>>>(x, ld_x, g, b, run_mean, run_var, momentum, static_cast<float*>(y), save_mean, save_rstd, rows, dim);
+    launch_pdl(bn_train_fwd_kernel<float>, ceil_div(dim, 32), 256, 0, st, x, ld_x, g, b, run_mean, run_var, momentum, static_cast<float*>(y), save_mean, save_rstd, rows, dim);
   AVF_LAUNCH_CHECK("bn_train_fwd_kernel");
   return 0;
 }
@@ -630,7 +654,7 @@ int bn_train_fwd(int out_mode, const float* x, int ld_x, const float* g, const f
 int bn_bwd(const float* x, int ld_x, const float* dy, const float* g, const float* mean, const float* rstd_or_var, int batch_stats, float* dx,
            int ld_dx, float* dgamma, float* dbeta, int rows, int dim, cudaStream_t st) {
   AVF_REQUIRE(rows > 0 && x && dy && g && mean && rstd_or_var, AVF_EINVAL, "batch_norm_bwd: null pointer / rows=%d", rows);
-  bn_bwd_kernel<<<ceil_div(dim, 32), 256, 0, st>>>(x, ld_x, dy, g, mean, rstd_or_var, batch_stats, dx, ld_dx, dgamma, dbeta, rows, dim);
+  launch_pdl(bn_bwd_kernel, ceil_div(dim, 32), 256, 0, st, x, ld_x, dy, g, mean, rstd_or_var, batch_stats, dx, ld_dx, dgamma, dbeta, rows, dim);
   AVF_LAUNCH_CHECK("bn_bwd_kernel");
   return 0;
 }
@@ -643,7 +667,7 @@ int adam_step(float* p, const float* g, float* m, float* v, void* shadow, size_t
   AVF_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
               AVF_EINVAL, "adam_step: buckets must be 16-byte aligned");
   const double bc1 = 1.0 - pow(double(b1), step), bc2 = 1.0 - pow(double(b2), step);
-  adam_kernel<<<unsigned((n / 4 + 256) / 256), 256, 0, st>>>(p, g, m, v, static_cast<__nv_bfloat16*>(shadow), n, lr, b1, b2, eps, wd, float(1.0 / bc1),
+  launch_pdl(adam_kernel, unsigned((n / 4 + 256) / 256), 256, 0, st, p, g, m, v, static_cast<__nv_bfloat16*>(shadow), n, lr, b1, b2, eps, wd, float(1.0 / bc1),
                                                                float(1.0 / sqrt(bc2)), decoupled, grad_scale);
   AVF_LAUNCH_CHECK("adam_kernel");
   return 0;
