@@ -20,6 +20,26 @@ def _f32_dense(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+def _hand_over(params, grads):
+    """Gradient hand-over without one `add` launch per parameter: when every parameter that receives a gradient here already
+    owns an fp32 ``.grad`` buffer of the right shape on the GPU (FusedAdam keeps them as views of its flat bucket), all the
+    gradients are accumulated into those buffers with ONE multi-tensor launch and the Function returns None for them (autograd
+    then has nothing to accumulate) — the AU_former front alone has 27 small parameters.  Otherwise the gradients are
+    returned unchanged and autograd's AccumulateGrad does what it always does."""
+    dst, src = [], []
+    for prm, g in zip(params, grads):
+        if g is None:
+            continue
+        pg = prm.grad
+        if pg is None or pg.dtype != torch.float32 or not pg.is_cuda or pg.shape != g.shape or not g.is_cuda:
+            return list(grads)
+        dst.append(pg)
+        src.append(g if g.dtype == torch.float32 else g.float())
+    if dst:
+        torch._foreach_add_(dst, src)
+    return [None] * len(grads)
+
+
 class EncoderStackFn(torch.autograd.Function):
     """Transformer (models/heads.py:242-256) on an fp32 token matrix [n_seq*n_tok, dim]."""
 
@@ -54,6 +74,7 @@ class SFormerFn(torch.autograd.Function):
         y, tape = AF.encoder_stack_fwd_train(x, packed, shape, *ctx.drop)
         ctx.packed, ctx.shape_, ctx.tape, ctx.fshape, ctx.fdtype, ctx.pos_shape = packed, shape, tape, (F_, C, H, W), fmap.dtype, pos.shape
         ctx.params = params
+        ctx.pos_param = pos
         return AF.sformer_tokens_unpack(y, (F_, C, H, W), fmap.dtype)
 
     @staticmethod
@@ -68,6 +89,7 @@ class SFormerFn(torch.autograd.Function):
             dpos = torch.zeros(ctx.pos_shape, dtype=torch.float32, device=dx.device)
             dpos.view(-1, C)[: H * W] = AF.colsum(dx.view(F_, H * W * C)).view(H * W, C)
         dfmap = AF.sformer_tokens_unpack(dx, ctx.fshape, ctx.fdtype) if needs[0] else None
+        (dpos,) = _hand_over((ctx.pos_param,), (dpos,))
         return (dfmap, dpos, None, *grads)
 
 
@@ -77,6 +99,7 @@ class TFormerEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, frames, cls_token, pos, n_frames):
         ctx.meta = (frames.shape, frames.dtype, n_frames, cls_token.shape, pos.shape)
+        ctx.params = (cls_token, pos)
         return AF.tformer_embed(frames.detach(), cls_token.detach().reshape(-1), pos.detach()[0], n_frames)
 
     @staticmethod
@@ -93,6 +116,7 @@ class TFormerEmbedFn(torch.autograd.Function):
             s = AF.colsum(dtok.view(n_clips, (T + 1) * dim))
             dpos = s.view(pshape) if needs[2] else None
             dcls = s[:dim].clone().view(cshape) if needs[1] else None
+        dcls, dpos = _hand_over(ctx.params, (dcls, dpos))
         return dframes, dcls, dpos, None
 
 
@@ -114,6 +138,7 @@ class AUFrontFn(torch.autograd.Function):
             bn.num_batches_tracked += 1
         ctx.saved = (emb_d, f, bn, batch_stats, tape, n_clips, pos.shape, emb.shape, emb.dtype)
         ctx.save_for_backward(bn_w)
+        ctx.params = (bn_w, bn_b, pos) + tuple(wb)
         return x
 
     @staticmethod
@@ -131,7 +156,8 @@ class AUFrontFn(torch.autograd.Function):
             wb_grads.append(dbc[i * emb_dim:(i + 1) * emb_dim] if needs[7 + 2 * i] else None)
         if demb is not None:
             demb = demb.view(emb_shape).to(emb_dtype)
-        return (demb, dg if needs[1] else None, db if needs[2] else None, dbc.view(pos_shape).clone() if needs[3] else None, None, None, *wb_grads)
+        pg = _hand_over(ctx.params, [dg if needs[1] else None, db if needs[2] else None, dbc.view(pos_shape).clone() if needs[3] else None] + wb_grads)
+        return (demb, pg[0], pg[1], pg[2], None, None, *pg[3:])
 
 
 class AddPosFn(torch.autograd.Function):
@@ -140,6 +166,7 @@ class AddPosFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, pos, period):
         ctx.meta = (pos.shape, period)
+        ctx.params = (pos,)
         y = _f32_dense(x.detach()).clone()
         return AF.add_row_periodic_(y, pos.detach().reshape(period, -1), period)
 
@@ -151,6 +178,7 @@ class AddPosFn(torch.autograd.Function):
         if needs[1]:
             d = _f32_dense(dy)
             dpos = AF.colsum(d.view(d.shape[0] // period, period * d.shape[1])).view(pshape)
+        (dpos,) = _hand_over(ctx.params, (dpos,))
         return (dy if needs[0] else None), dpos, None
 
 
@@ -162,6 +190,7 @@ class AULogitsFn(torch.autograd.Function):
         last = head._packed_last()
         tok = _f32_dense(tokens.detach())
         ctx.saved = (tok, last, n_clips)
+        ctx.params = tuple(w12)
         return AF.au_logits(tok, last.w, n_clips)
 
     @staticmethod
@@ -171,4 +200,5 @@ class AULogitsFn(torch.autograd.Function):
         d = dout21 if (dout21.dtype == torch.float32 and dout21.stride(-1) == 1) else dout21.float().contiguous()
         want_dw = any(needs[3:])
         dx, dw = AF.au_logits_bwd(d, tok, last.w, n_clips, want_dx=needs[0], want_dw=want_dw)
-        return (dx, None, None, *[(dw[i:i + 1] if needs[3 + i] else None) for i in range(12)])
+        pg = _hand_over(ctx.params, [(dw[i:i + 1] if needs[3 + i] else None) for i in range(12)])
+        return (dx, None, None, *pg)
