@@ -194,6 +194,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # The gathers are tiny ([512, 21] fp32 per rank): one or two NCCL channels are plenty, and every channel is a CTA that sits
+        # on an SM while the collective waits for the slowest rank.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     T, B = N_FRAMES, CLIPS_PER_GPU
 
@@ -246,7 +249,15 @@ def run_ours(args):
         sm_split = None
         if os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
             sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
+        # N > 1: the asynchronous gather of batch i runs while batch i+1 computes.  A persistent kernel with one CTA per SM would find
+        # the SMs of the NCCL CTAs taken, and the displaced CTAs (static tile striding) would finish late: leave those SMs out of the
+        # persistent grids (4096 SFormer tiles are 28 per CTA on 146 CTAs as on 148).
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_reserve = int(os.environ.get("AVF_SM_RESERVE", "2" if world > 1 else "0"))
+        if sm_reserve > 0:
+            L.avf_set_sm_cap(n_sm - sm_reserve)
         graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split)
+        L.avf_set_sm_cap(0)
 
         pipe = A.dp.PipelinedLogitGather()       # N > 1: the gather of batch i runs under the kernels of batch i+1
 
