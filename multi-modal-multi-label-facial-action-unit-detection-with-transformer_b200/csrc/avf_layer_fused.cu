@@ -71,7 +71,7 @@ constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, T
 
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
-  B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_HBUF_FREE, B_HBUF_FREE1, B_X2_FULL,
+  B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_X2_FULL,
   B_QR_FULL, B_QR_EMPTY = B_QR_FULL + QRING, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, NUM_BARS
 };
 static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
