@@ -99,6 +99,9 @@ int         avf_debug_fused_prof(uint64_t* out64, int reset);
 /* Developer aid: `host_mapped_words` = 4 uint32 in pinned (device-visible) host memory, or NULL.  A wait inside the fused
  * kernel that times out (a protocol bug) writes {block, thread, barrier index, parity} there before it traps. */
 int         avf_debug_set_trap_buffer(void* host_mapped_words);
+/* Developer aid: 16 %globaltimer stamps (ns) of CTA 0 of the last tcgen05 GEMM launch when the library is built with
+ * -DAVF_GEMM_PROF (tools/gemm_phases.py); AVF_EUNSUPPORTED otherwise. */
+int         avf_debug_gemm_prof(uint64_t* out16);
 
 /* ---- workspace ---------------------------------------------------------------------------- */
 /* Bytes of scratch avf_encoder_stack_fwd needs for this shape/mode (replaces the implicit ATen

@@ -96,6 +96,7 @@ SIGNATURES = {
     "avf_set_sm_cap": (ctypes.c_int, [ctypes.c_int]),
     "avf_set_pdl_enabled": (ctypes.c_int, [ctypes.c_int]),
     "avf_debug_set_trap_buffer": (ctypes.c_int, [_c_p]),
+    "avf_debug_gemm_prof": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
     "avf_layernorm_bwd_workspace_bytes": (_sz, [_i32, _i32]),

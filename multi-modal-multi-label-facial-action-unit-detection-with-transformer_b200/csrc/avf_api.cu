@@ -164,6 +164,8 @@ int avf_encoder_fused_supported(const avf_stack_shape* s, int mode) {
 /* Debug: per-phase cycle counters of the fused encoder kernel (library built with -DAVF_FUSED_PROF); else AVF_EUNSUPPORTED. */
 int avf_debug_fused_prof(uint64_t* out64, int reset) { return fused_prof_read(reinterpret_cast<unsigned long long*>(out64), reset); }
 
+int avf_debug_gemm_prof(uint64_t* out16) { return gemm_prof_read(reinterpret_cast<unsigned long long*>(out16)); }
+
 int avf_debug_set_trap_buffer(void* host_mapped_words) { return fused_set_trap_buffer(host_mapped_words); }
 
 int avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05) {

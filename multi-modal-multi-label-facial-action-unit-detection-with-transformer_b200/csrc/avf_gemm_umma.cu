@@ -44,15 +44,38 @@ struct GemmCfg {
 };
 
 // Epilogue math on one 32-column chunk held in registers, then the store of that chunk.
+// 4 x 4 transpose of 16-byte pieces inside every quad of lanes: lane j of a quad enters with pieces 0..3 of ITS row and leaves
+// with piece j of the rows of lanes 0..3 of the quad.  A store instruction then writes 64 contiguous bytes per row (8 rows =
+// 8 lines per instruction) instead of 16 bytes in each of 32 rows: the tile write-back was bound by the number of memory
+// transactions, not by bytes (CTA milestones: 4 us per 128 x 256 bf16 tile, the main loop of the next tile starved behind it).
+__device__ __forceinline__ void quad_transpose(uint4 (&p)[4], int lane) {
+  auto xchg = [&](uint4& keep_lo, uint4& keep_hi, bool upper, int mask) {     // lower lane sends keep_hi, upper lane sends keep_lo
+    uint4 snd = upper ? keep_lo : keep_hi, rcv;
+    rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, mask);
+    rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, mask);
+    rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, mask);
+    rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, mask);
+    if (upper) keep_lo = rcv; else keep_hi = rcv;
+  };
+  const bool b0 = lane & 1, b1 = lane & 2;
+  xchg(p[0], p[1], b0, 1);
+  xchg(p[2], p[3], b0, 1);
+  xchg(p[0], p[2], b1, 2);
+  xchg(p[1], p[3], b1, 2);
+}
+
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
                                                const float* __restrict__ bias, const float* res, int ld_res, int flags,
-                                               __nv_bfloat16* aux, int ld_aux, const DropSpec& drop, int n_total,
+                                               __nv_bfloat16* aux, int ld_aux, const DropSpec& drop, int n_total, int M,
                                                const float4* pre_res = nullptr) {
+  // every lane of the warp runs this (the store below shuffles between lanes); rows beyond M only skip their memory accesses
+  const bool valid = row < M;
+  const int lane = threadIdx.x & 31;
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (flags & AVF_EPI_DGELU) {       // backward of the tanh-GELU: multiply by gelu'(pre-activation)
+  if ((flags & AVF_EPI_DGELU) && valid) {       // backward of the tanh-GELU: multiply by gelu'(pre-activation)
     const __nv_bfloat16* ap = aux + size_t(row) * ld_aux + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -72,7 +95,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
       f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
     }
   }
-  if (flags & AVF_EPI_SAVE_PRE) {    // training forward: keep the pre-activation (bf16) for the GELU backward
+  if ((flags & AVF_EPI_SAVE_PRE) && valid) {    // training forward: keep the pre-activation (bf16) for the GELU backward
     __nv_bfloat16* ap = aux + size_t(row) * ld_aux + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
@@ -93,7 +116,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= drop_factor(drop, i0 + j);
   }
-  if (flags & AVF_EPI_RESIDUAL) {
+  if ((flags & AVF_EPI_RESIDUAL) && valid) {
     const float* rp = res + size_t(row) * ld_res + col0;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -101,23 +124,49 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
       f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
     }
   }
-  OutT* cp = C + size_t(row) * ldc + col0;
+  const int row_q = row - (lane & 3);            // first row of this lane's quad
   if constexpr (sizeof(OutT) == 4) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(cp) + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-  } else {
+    for (int h = 0; h < 2; ++h) {                // two halves of 16 columns = 4 pieces of 16 bytes
+      uint4 p[4];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 o;
-      o.x = pack_bf16x2(f[j], f[j + 1]);
-      o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-      o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-      o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(cp) + j) = o;
+      for (int j = 0; j < 4; ++j)
+        p[j] = make_uint4(__float_as_uint(f[h * 16 + 4 * j]), __float_as_uint(f[h * 16 + 4 * j + 1]), __float_as_uint(f[h * 16 + 4 * j + 2]),
+                          __float_as_uint(f[h * 16 + 4 * j + 3]));
+      quad_transpose(p, lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (row_q + i < M) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(C) + size_t(row_q + i) * ldc + col0 + h * 16 + (lane & 3) * 4) = p[i];
     }
+  } else {
+    uint4 p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      p[j].x = pack_bf16x2(f[8 * j], f[8 * j + 1]);
+      p[j].y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+      p[j].z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+      p[j].w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    }
+    quad_transpose(p, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (row_q + i < M) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + size_t(row_q + i) * ldc + col0 + (lane & 3) * 8) = p[i];
   }
 }
+
+// Developer build -DAVF_GEMM_PROF: CTA 0 stamps %globaltimer (ns) at the milestones of its life into g_gemm_prof[16].
+#ifdef AVF_GEMM_PROF
+__device__ unsigned long long g_gemm_prof[16];
+__device__ __forceinline__ void gprof(int i) {
+  if (blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_gemm_prof[i] = t;
+  }
+}
+#else
+__device__ __forceinline__ void gprof(int) {}
+#endif
 
 // Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 // (n-block fastest, so CTAs that run concurrently share the A tile in L2).  The TMEM accumulator is double
@@ -138,6 +187,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) gprof(0);                  // kernel entry
   const int kblocks_total = (K + BK - 1) / BK;     // a ragged last block is zero-filled by TMA
   const int kb_per_split = (kblocks_total + splits - 1) / splits;
   const int n_blocks = N / BN;
@@ -165,8 +215,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) gprof(1);                  // prologue done
   pdl_wait();        // the prologue above overlapped the previous kernel; its results are needed from here on
   pdl_trigger();
+  if (threadIdx.x == 0) gprof(2);                  // predecessor complete
 
   // Warps 0 and 1 run their loops with all 32 lanes on warp-uniform values (addresses, descriptors and loop state then live in
   // uniform registers and the issue loops are a few instructions per TMA / MMA); only the elected lane issues.
@@ -219,6 +271,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (leader && it == 0) gprof(3);         // first operand stage has landed
           const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
           // K-major: +32 bytes per UMMA_K inside the 128B swizzle span.  MN-major: 16 K-rows of 128 B = +2048 bytes,
           // panels of 64 MN elements 8192 B apart (LBO), 8-row groups 1024 B apart (SBO).
@@ -231,6 +284,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (leader) umma_commit(&empty_bar[s]); // frees the smem stage when these MMAs have read it
         }
         if (leader) umma_commit(&acc_full[buf]);  // accumulator complete
+        if (leader) gprof(4 + min(int(lt), 3));    // all MMAs of tile lt issued
       }
     }
   } else if (warp >= 4) {
@@ -269,6 +323,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after();
+        if (threadIdx.x == 128) gprof(8 + min(int(lt), 3));   // accumulator of tile lt complete
 #pragma unroll
         for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
           uint32_t v[32];
@@ -279,12 +334,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
-          if (row < M)
-            epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N, want_res ? &pre[c0 / 4] : nullptr);
+          epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N, M, want_res ? &pre[c0 / 4] : nullptr);
         }
       } else {
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after();
+        if (threadIdx.x == 128) gprof(8 + min(int(lt), 3));   // accumulator of tile lt complete
 #pragma unroll 1
         for (int c0 = 0; c0 < HALF_COLS; c0 += 32) {
           uint32_t v[32];
@@ -295,15 +350,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
-          if (row < M) epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N);
+          epilogue_chunk<OutT>(v, row, n0 + half * HALF_COLS + c0, Cs, ldc, bias_t, res, ld_res, flags, aux, ld_aux, drop, N, M);
         }
       }
     }
   }
 
+  if (threadIdx.x == 128) gprof(12);               // epilogue warp 0 done
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) gprof(13);                 // kernel end
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,6 +532,17 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
   AVF_GEMM(64, 8, true)
 #undef AVF_GEMM
   return AVF_EUNSUPPORTED;
+}
+
+int gemm_prof_read(unsigned long long* out16) {
+#ifdef AVF_GEMM_PROF
+  AVF_CUDA(cudaDeviceSynchronize());
+  AVF_CUDA(cudaMemcpyFromSymbol(out16, g_gemm_prof, sizeof(unsigned long long) * 16));
+  return 0;
+#else
+  (void)out16;
+  return AVF_EUNSUPPORTED;
+#endif
 }
 
 size_t gemm_umma_workspace_bytes(int m, int n, int k) {       // for the TN (wgrad) form
