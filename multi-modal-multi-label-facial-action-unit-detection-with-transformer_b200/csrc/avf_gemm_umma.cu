@@ -64,6 +64,19 @@ __device__ __forceinline__ void quad_transpose(uint4 (&p)[4], int lane) {
   xchg(p[1], p[3], b1, 2);
 }
 
+// The lane's own 16 fp32 columns [col, col + 16) of `src` (row pitch ld), fetched the same way: lane j of a quad reads piece j of
+// the quad's four rows (64 contiguous bytes per row per instruction), then the quad transposes.  Rows beyond M read nothing.
+__device__ __forceinline__ void quad_load16(const float* src, int ld, int row, int col, int M, int lane, float4 (&out)[4]) {
+  const int row_q = row - (lane & 3);
+  uint4 p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    p[i] = row_q + i < M ? *reinterpret_cast<const uint4*>(src + size_t(row_q + i) * ld + col + (lane & 3) * 4) : make_uint4(0u, 0u, 0u, 0u);
+  quad_transpose(p, lane);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[j] = make_float4(__uint_as_float(p[j].x), __uint_as_float(p[j].y), __uint_as_float(p[j].z), __uint_as_float(p[j].w));
+}
+
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row, int col0, OutT* C, int ldc,
                                                const float* __restrict__ bias, const float* res, int ld_res, int flags,
@@ -116,11 +129,15 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int row,
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= drop_factor(drop, i0 + j);
   }
-  if ((flags & AVF_EPI_RESIDUAL) && valid) {
-    const float* rp = res + size_t(row) * ld_res + col0;
+  if (flags & AVF_EPI_RESIDUAL) {       // (warp-uniform: the un-prefetched form shuffles between lanes)
+    float4 r8[8];
+    if (pre_res == nullptr) {
+      quad_load16(res, ld_res, row, col0, M, lane, reinterpret_cast<float4(&)[4]>(r8[0]));
+      quad_load16(res, ld_res, row, col0 + 16, M, lane, reinterpret_cast<float4(&)[4]>(r8[4]));
+    }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 r = pre_res != nullptr ? pre_res[j >> 2] : *reinterpret_cast<const float4*>(rp + j);
+      const float4 r = pre_res != nullptr ? pre_res[j >> 2] : r8[j >> 2];
       f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
     }
   }
@@ -315,11 +332,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // Narrow tiles are epilogue-latency bound (K is short on this path): request the thread's residual fragment BEFORE
         // waiting for the accumulator, so that the HBM/L2 round trip overlaps the main loop of this tile.
         float4 pre[HALF_COLS / 4];
-        const bool want_res = (flags & AVF_EPI_RESIDUAL) && row < M;
+        const bool want_res = (flags & AVF_EPI_RESIDUAL) != 0;      // warp-uniform: the fetch shuffles inside lane quads
         if (want_res) {
-          const float4* rp = reinterpret_cast<const float4*>(res + size_t(row) * ld_res + n0 + half * HALF_COLS);
 #pragma unroll
-          for (int j = 0; j < HALF_COLS / 4; ++j) pre[j] = rp[j];
+          for (int j = 0; j < HALF_COLS / 16; ++j)
+            quad_load16(res, ld_res, row, n0 + half * HALF_COLS + j * 16, M, lane, reinterpret_cast<float4(&)[4]>(pre[4 * j]));
         }
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after();
