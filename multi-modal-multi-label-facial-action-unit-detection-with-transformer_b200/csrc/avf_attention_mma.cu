@@ -24,6 +24,17 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(smem_row_ptr)));
 }
 
+// 4 x 4 transpose of 32-bit words inside every quad of lanes: lane t enters with words 0..3 of ITS 16-byte chunk and leaves
+// with word t of the chunks of lanes 0..3 (and back: the transpose is its own inverse).
+__device__ __forceinline__ void quad_transpose32(uint32_t (&p)[4], int lane) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  uint32_t r;
+  r = __shfl_xor_sync(0xffffffffu, b0 ? p[0] : p[1], 1); if (b0) p[0] = r; else p[1] = r;
+  r = __shfl_xor_sync(0xffffffffu, b0 ? p[2] : p[3], 1); if (b0) p[2] = r; else p[3] = r;
+  r = __shfl_xor_sync(0xffffffffu, b1 ? p[0] : p[2], 2); if (b1) p[0] = r; else p[2] = r;
+  r = __shfl_xor_sync(0xffffffffu, b1 ? p[1] : p[3], 2); if (b1) p[1] = r; else p[3] = r;
+}
+
 template <int DH, int NP>    // NP = tokens padded to a multiple of 16 (16 / 32 / 48 / 64)
 __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                                                             int n_problems, int n_tok, int heads, float scale_log2e, int q_rows) {
@@ -64,16 +75,29 @@ __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(cons
   for (int mt = 0; mt < NP / 16; ++mt) {
     if (mt * 16 >= q_rows) break;
     const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
-    // Q fragments (A operand, row-major 16x16 per k-step) straight from global
+    // Q fragments (A operand, row-major 16x16 per k-step) from global: lane t of a quad fetches the 16-byte chunks t, t+4, ... of
+    // its two rows (the quad reads 64 contiguous bytes per row and instruction instead of 4 x 4 bytes), then the quad transposes
+    // 4-byte pieces so that every lane holds columns 2t, 2t+1 of each 8-column chunk — the m16n8k16 A layout.
     uint32_t qf[DH / 16][4];
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) {
-      const __nv_bfloat16* qlo = base + size_t(r_lo) * (3 * inner) + ks * 16 + 2 * t;
-      const __nv_bfloat16* qhi = base + size_t(r_hi) * (3 * inner) + ks * 16 + 2 * t;
-      qf[ks][0] = r_lo < n_tok ? *reinterpret_cast<const uint32_t*>(qlo) : 0u;
-      qf[ks][1] = r_hi < n_tok ? *reinterpret_cast<const uint32_t*>(qhi) : 0u;
-      qf[ks][2] = r_lo < n_tok ? *reinterpret_cast<const uint32_t*>(qlo + 8) : 0u;
-      qf[ks][3] = r_hi < n_tok ? *reinterpret_cast<const uint32_t*>(qhi + 8) : 0u;
+    for (int grp = 0; grp < DH / 32; ++grp) {
+      uint32_t lo[4] = {0u, 0u, 0u, 0u}, hi[4] = {0u, 0u, 0u, 0u};
+      if (r_lo < n_tok) {
+        const uint4 v = *reinterpret_cast<const uint4*>(base + size_t(r_lo) * (3 * inner) + (grp * 4 + t) * 8);
+        lo[0] = v.x; lo[1] = v.y; lo[2] = v.z; lo[3] = v.w;
+      }
+      if (r_hi < n_tok) {
+        const uint4 v = *reinterpret_cast<const uint4*>(base + size_t(r_hi) * (3 * inner) + (grp * 4 + t) * 8);
+        hi[0] = v.x; hi[1] = v.y; hi[2] = v.z; hi[3] = v.w;
+      }
+      quad_transpose32(lo, lane);
+      quad_transpose32(hi, lane);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {               // piece t of chunk grp*4 + j = columns (grp*4 + j)*8 + 2t, +1
+        const int ks = (grp * 4 + j) >> 1, half = (grp * 4 + j) & 1;
+        qf[ks][half * 2] = lo[j];
+        qf[ks][half * 2 + 1] = hi[j];
+      }
     }
     // S = Q K^T  (B fragment: B[k][n] = K[n][k] -> one 32-bit load per register)
     float s[NP / 8][4];
@@ -135,12 +159,20 @@ __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(cons
       }
     }
     const float i_lo = 1.f / l_lo, i_hi = 1.f / l_hi;
-    __nv_bfloat16* olo = out + (size_t(seq) * q_rows + r_lo) * inner + head * DH + 2 * t;
-    __nv_bfloat16* ohi = out + (size_t(seq) * q_rows + r_hi) * inner + head * DH + 2 * t;
+    __nv_bfloat16* olo = out + (size_t(seq) * q_rows + r_lo) * inner + head * DH;
+    __nv_bfloat16* ohi = out + (size_t(seq) * q_rows + r_hi) * inner + head * DH;
 #pragma unroll
-    for (int nt = 0; nt < DH / 8; ++nt) {
-      if (r_lo < q_rows) *reinterpret_cast<uint32_t*>(olo + nt * 8) = pack_bf16x2(o[nt][0] * i_lo, o[nt][1] * i_lo);
-      if (r_hi < q_rows) *reinterpret_cast<uint32_t*>(ohi + nt * 8) = pack_bf16x2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+    for (int grp = 0; grp < DH / 32; ++grp) {     // the same transpose backwards: lane t stores the whole 16-byte chunk grp*4 + t
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lo[j] = pack_bf16x2(o[grp * 4 + j][0] * i_lo, o[grp * 4 + j][1] * i_lo);
+        hi[j] = pack_bf16x2(o[grp * 4 + j][2] * i_hi, o[grp * 4 + j][3] * i_hi);
+      }
+      quad_transpose32(lo, lane);
+      quad_transpose32(hi, lane);
+      if (r_lo < q_rows) *reinterpret_cast<uint4*>(olo + (grp * 4 + t) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (r_hi < q_rows) *reinterpret_cast<uint4*>(ohi + (grp * 4 + t) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
   }
 }
