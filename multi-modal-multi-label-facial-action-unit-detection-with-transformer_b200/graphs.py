@@ -35,10 +35,12 @@ class GraphedHotPath:
     host-to-device), outputs are the graph's static tensors (valid until the next replay)."""
 
     def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor, sm_split=None):
-        """sm_split = (sformer_sms, chain_sms): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the TFormer /
-        AU_former / fusion-head chain, whose persistent GEMMs are capped at `chain_sms` CTAs (every persistent CTA of either
-        family owns a whole SM, so the two grids partition the GPU).  None = the two run one after the other on all SMs.
-        Default from the environment variable AVF_SM_SPLIT="s,c"."""
+        """sm_split = (sformer_sms, chain_sms[, frames_beside]): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the
+        TFormer / AU_former / fusion-head chain, whose persistent GEMMs are capped at `chain_sms` CTAs (every persistent CTA of
+        either family owns a whole SM, so the two grids partition the GPU).  With `frames_beside` only that many leading
+        stage-3 maps go through the side-by-side launch — sized to last about as long as the chain, half of whose kernels
+        (fusion head: 64 CTAs, AU_former GEMMs: 32-96) leave SMs idle — and the rest follows on all SMs.
+        None = the two run one after the other on all SMs.  Default from the environment variable AVF_SM_SPLIT="s,c[,f]"."""
         if model.training:
             raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
         if sm_split is None and os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
@@ -67,8 +69,10 @@ class GraphedHotPath:
             # branch: the SFormer (independent of the chain below) on its own share of the SMs
             self.side2.wait_stream(cur)
             old_cap = L.avf_set_sm_cap(self.sm_split[0])
+            n_beside = self.stage3.shape[0] if len(self.sm_split) < 3 else min(int(self.sm_split[2]), self.stage3.shape[0])
+            s_out = torch.empty_like(self.stage3)
             with torch.cuda.stream(self.side2):
-                s_out = vm.s_former.sformer(self.stage3)
+                vm.s_former.sformer(self.stage3[:n_beside], out=s_out[:n_beside])
             L.avf_set_sm_cap(self.sm_split[1])
         # branch: the audio AU_former is independent of everything up to the fusion head
         self.side.wait_stream(cur)
@@ -81,6 +85,8 @@ class GraphedHotPath:
         if self.sm_split is not None:
             L.avf_set_sm_cap(old_cap)
             cur.wait_stream(self.side2)
+            if n_beside < self.stage3.shape[0]:
+                vm.s_former.sformer(self.stage3[n_beside:], out=s_out[n_beside:])
         else:
             s_out = vm.s_former.sformer(self.stage3)
         return s_out, out21, dec

@@ -390,7 +390,7 @@ def test_train_mode_model_uses_dropout_and_stays_finite():
 # ---------------------------------------------------------------------------------------------
 # CUDA-graph front ends
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("sm_split", [None, (100, 40)])
+@pytest.mark.parametrize("sm_split", [None, (100, 40), (64, 84, 64)])
 def test_graphed_hot_path_equals_eager(sm_split):
     """sm_split: the persistent SFormer kernel on its own share of the SMs next to the TFormer / head chain (avf_set_sm_cap);
     results must not depend on the partition, and the cap must be restored afterwards."""
@@ -408,6 +408,26 @@ def test_graphed_hot_path_equals_eager(sm_split):
             s_out, o, d = g.replay(*dev)
             torch.cuda.synchronize()
             assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """Every kernel is launched with the programmatic-stream-serialization attribute and waits (griddepcontrol.wait) for its
+    predecessor before touching memory: results must be bit-identical to plain launches (avf_set_pdl_enabled(0))."""
+    T, B, seed = 16, 5, 67
+    m = _model(seed, T, "bf16").eval()
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    dev = (stage3.bfloat16().cuda(), frame.bfloat16().cuda(), audio.cuda())
+    L = A._lib.lib()
+    with torch.no_grad():
+        old = L.avf_set_pdl_enabled(0)
+        try:
+            ref = [t.clone() for t in m.hot_path(*dev, want_decisions=True)]
+        finally:
+            L.avf_set_pdl_enabled(old)
+        for _ in range(3):
+            got = m.hot_path(*dev, want_decisions=True)
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(ref, got))
 
 
 def test_graphed_train_step_follows_eager_training():
