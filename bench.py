@@ -358,7 +358,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(),
             "clocks": clocks.summary(),
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e, "note": "model.hot_path_from_host() on pinned host buffers: chunked H2D of all inputs on a copy stream overlapped with the kernels + D2H of logits/decisions"},
+                    "ms_per_step": ms_e2e, "note": "model.hot_path_from_host() on pinned host buffers: chunked H2D of all inputs on a copy stream overlapped with the kernels (two alternating device staging sets: the copies of step i+1 start under the kernels of step i) + D2H of logits/decisions"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline,

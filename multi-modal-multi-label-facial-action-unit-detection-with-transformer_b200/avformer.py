@@ -178,7 +178,8 @@ class TwoStreamAuralVisualFormer(nn.Module):
         compute stream first runs the TFormer / AU_former / fusion-head chain (whose small inputs are copied first) and then
         the fused SFormer kernel chunk by chunk, each launch waiting only for its own piece — so the kernels hide behind
         the PCIe transfer instead of queueing after it.  Logits (and int32 decisions) are copied back into ``out_host`` /
-        ``dec_host`` (pinned) when given.  Returns (sformer_out [device], out21 [device], decisions [device])."""
+        ``dec_host`` (pinned) when given.  Returns (sformer_out [device], out21 [device], decisions [device]); ``sformer_out``
+        lives in one of two alternating staging sets and stays valid until the call after the next one."""
         dev = self.au_head.pos_embedding.device
         if not dev.type == "cuda":
             raise RuntimeError("avformer_b200: the model is not on a CUDA device; the B200 path has no CPU fallback")
@@ -187,41 +188,49 @@ class TwoStreamAuralVisualFormer(nn.Module):
         if st is None or st["key"] != key:
             n = stage3_host.shape[0]
             bounds = [(n * i // chunks, n * (i + 1) // chunks) for i in range(chunks)]
+            bounds = [b for b in bounds if b[1] > b[0]]
+            # TWO sets of device staging buffers, used alternately: the host->device copies of call i+1 start while the kernels
+            # of call i still run (the copy stream only waits for the call that used the same set, two calls back), so that
+            # back-to-back calls keep the PCIe link busy without the ~0.2 ms tail of the last SFormer chunk in between.
             st = self._host_staging = {
-                "key": key, "bounds": [b for b in bounds if b[1] > b[0]],
-                "stage3": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
-                "s_out": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
-                "frame": torch.empty(frame_host.shape, dtype=frame_host.dtype, device=dev),
-                "audio": torch.empty(audio_host.shape, dtype=torch.float32, device=dev),
-                "copy_stream": torch.cuda.Stream(device=dev),
-                "ev_small": torch.cuda.Event(), "ev": [torch.cuda.Event() for _ in bounds],
+                "key": key, "bounds": bounds, "k": 0, "copy_stream": torch.cuda.Stream(device=dev),
+                "sets": [{
+                    "stage3": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
+                    "s_out": torch.empty(stage3_host.shape, dtype=stage3_host.dtype, device=dev),
+                    "frame": torch.empty(frame_host.shape, dtype=frame_host.dtype, device=dev),
+                    "audio": torch.empty(audio_host.shape, dtype=torch.float32, device=dev),
+                    "ev_small": torch.cuda.Event(), "ev": [torch.cuda.Event() for _ in bounds], "done": torch.cuda.Event(),
+                } for _ in range(2)],
             }
         main = torch.cuda.current_stream(dev)
         cs = st["copy_stream"]
-        cs.wait_stream(main)                                   # the previous call's kernels are done with the staging buffers
+        cur = st["sets"][st["k"] & 1]
+        st["k"] += 1
+        cs.wait_event(cur["done"])                             # the kernels of the call that last used this set (no-op the first time)
         with torch.cuda.stream(cs):
-            st["frame"].copy_(frame_host, non_blocking=True)
-            st["audio"].copy_(audio_host, non_blocking=True)
-            st["ev_small"].record(cs)
-            for (lo, hi), ev in zip(st["bounds"], st["ev"]):
-                st["stage3"][lo:hi].copy_(stage3_host[lo:hi], non_blocking=True)
+            cur["frame"].copy_(frame_host, non_blocking=True)
+            cur["audio"].copy_(audio_host, non_blocking=True)
+            cur["ev_small"].record(cs)
+            for (lo, hi), ev in zip(st["bounds"], cur["ev"]):
+                cur["stage3"][lo:hi].copy_(stage3_host[lo:hi], non_blocking=True)
                 ev.record(cs)
         vm = self.video_model.video_model
-        main.wait_event(st["ev_small"])
-        cls = vm.t_former.cls_features(st["frame"])
+        main.wait_event(cur["ev_small"])
+        cls = vm.t_former.cls_features(cur["frame"])
         n_clips = cls.shape[0]
         fused = torch.empty((n_clips * 12, 256), dtype=torch.float32, device=dev)
-        self.audio_model.au_head.tokens_into(st["audio"], st["audio"].shape[1], n_clips, out=fused, ld_out=256)
+        self.audio_model.au_head.tokens_into(cur["audio"], cur["audio"].shape[1], n_clips, out=fused, ld_out=256)
         self.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         out21, dec = self.au_head.logits21_(fused, n_clips, True)
         if out_host is not None:
             out_host.copy_(out21, non_blocking=True)
         if dec_host is not None:
             dec_host.copy_(dec, non_blocking=True)
-        for (lo, hi), ev in zip(st["bounds"], st["ev"]):
+        for (lo, hi), ev in zip(st["bounds"], cur["ev"]):
             main.wait_event(ev)
-            vm.s_former.sformer(st["stage3"][lo:hi], out=st["s_out"][lo:hi])
-        return st["s_out"], out21, dec
+            vm.s_former.sformer(cur["stage3"][lo:hi], out=cur["s_out"][lo:hi])
+        cur["done"].record(main)
+        return cur["s_out"], out21, dec
 
     # -- loss helpers (models/avformer.py:108-123) ------------------------------------------------
     def get_au_loss(self, y_pred, y_true):

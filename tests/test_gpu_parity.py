@@ -244,6 +244,21 @@ def test_hot_path_from_host_matches_device_path():
             torch.cuda.synchronize()
             assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
             assert torch.equal(out_host, o_ref.cpu()) and torch.equal(dec_host, d_ref.cpu())
+        # back to back WITHOUT a synchronize in between (the two staging sets alternate; a result stays valid for one more call)
+        hs, refs = [], []
+        for it in range(4):
+            stage3, frame, audio = O.synth_hot_path_inputs(seed + 10 + it, B, T)
+            hs.append((stage3.bfloat16().pin_memory(), frame.bfloat16().pin_memory(), audio.pin_memory()))
+            refs.append(m.hot_path(hs[-1][0].cuda(), hs[-1][1].cuda(), hs[-1][2].cuda(), want_decisions=True))
+        torch.cuda.synchronize()
+        prev = None
+        for it in range(4):
+            got = m.hot_path_from_host(*hs[it], chunks=5)
+            if prev is not None:                       # the previous call's outputs are still intact
+                assert all(torch.equal(a, b) for a, b in zip(prev, refs[it - 1]))
+            prev = got
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(prev, refs[3]))
 
 
 @pytest.mark.parametrize("B", [1, 2, 5, 33])
