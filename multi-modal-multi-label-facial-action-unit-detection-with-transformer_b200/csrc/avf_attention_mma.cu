@@ -57,16 +57,26 @@ __global__ void __launch_bounds__(DH == 32 ? 128 : 64) attention_mma_kernel(cons
 
   // stage K and V (zero rows beyond n_tok: 0 * garbage must not become NaN in P*V)
   constexpr int CH = DH / 8;                          // 16-byte chunks per row
-  for (int i = lane; i < NP * CH; i += 32) {
-    const int r = i / CH, c = i - r * CH;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+  // (all global loads are issued before the first shared-memory store: the warp has nothing else to hide their latency with)
+  constexpr int NLD = NP * CH / 32;
+  static_assert(NP * CH % 32 == 0, "whole warps of 16-byte chunks");
+  uint4 kreg[NLD], vreg[NLD];
+#pragma unroll
+  for (int u = 0; u < NLD; ++u) {
+    const int i = lane + u * 32, r = i / CH, c = i - r * CH;
+    kreg[u] = make_uint4(0, 0, 0, 0);
+    vreg[u] = make_uint4(0, 0, 0, 0);
     if (r < n_tok) {
       const __nv_bfloat16* p = base + size_t(r) * (3 * inner) + c * 8;
-      kv = *reinterpret_cast<const uint4*>(p + inner);
-      vv = *reinterpret_cast<const uint4*>(p + 2 * inner);
+      kreg[u] = *reinterpret_cast<const uint4*>(p + inner);
+      vreg[u] = *reinterpret_cast<const uint4*>(p + 2 * inner);
     }
-    *reinterpret_cast<uint4*>(&Ks[r][c * 8]) = kv;
-    *reinterpret_cast<uint4*>(&Vs[r][c * 8]) = vv;
+  }
+#pragma unroll
+  for (int u = 0; u < NLD; ++u) {
+    const int i = lane + u * 32, r = i / CH, c = i - r * CH;
+    *reinterpret_cast<uint4*>(&Ks[r][c * 8]) = kreg[u];
+    *reinterpret_cast<uint4*>(&Vs[r][c * 8]) = vreg[u];
   }
   __syncwarp();
 
