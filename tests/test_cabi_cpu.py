@@ -42,6 +42,19 @@ def test_no_device_means_error_not_fallback():
         m(torch.zeros(1, 12, 128))
 
 
+def test_launch_policy_switches_round_trip_without_a_device():
+    """avf_set_sm_cap / avf_set_pdl_enabled / avf_set_fused_enabled are plain process-wide switches (no device needed): each call
+    returns the previous value; the developer probes report 'unsupported' in a product build."""
+    L = A._lib.lib()
+    assert L.avf_set_sm_cap(116) == 0 and L.avf_set_sm_cap(-5) == 116 and L.avf_set_sm_cap(0) == 0
+    old = L.avf_set_pdl_enabled(0)
+    assert old in (0, 1) and L.avf_set_pdl_enabled(1) == 0 and L.avf_set_pdl_enabled(old) == 1
+    prev = L.avf_set_fused_enabled(0)
+    assert L.avf_set_fused_enabled(prev) == 0
+    buf = (ctypes.c_uint64 * 64)()
+    assert L.avf_debug_gemm_prof(buf) != 0 or torch.cuda.is_available()
+
+
 def test_state_dict_contract_matches_reference_names():
     m = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU")
     spec = {k: s for k, s, _ in O.state_dict_spec(16)}
