@@ -170,11 +170,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// The same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires, so a
+// waiting warp issues (almost) no instructions and leaves its scheduler's issue slots to the warps that have work.
+#ifndef AVF_SPIN_HINT_NS
+#define AVF_SPIN_HINT_NS 20000
+#endif
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity) {
+#if AVF_SPIN_HINT_NS > 0
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(uint32_t(AVF_SPIN_HINT_NS))
+      : "memory");
+  return ok != 0;
+#else
+  return mbar_try_wait(bar, parity);
+#endif
+}
 // Bounded wait: a protocol bug traps (-> a CUDA error the host reports) instead of hanging the GPU.  The spin loop
 // lives out of line so that the many wait sites of the fused kernels stay small.
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
       printf("avf: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
       __trap();

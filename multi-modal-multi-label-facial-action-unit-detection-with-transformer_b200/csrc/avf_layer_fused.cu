@@ -20,8 +20,10 @@
 // (one thread), 2 = TMA producer of the QKV ring, 3.. = row workers (warp w owns TMEM lanes 32*(w%4)..+31; the NSPLIT warps
 // of a lane quarter split the columns).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "avf_common.cuh"
+#include "avf_fused_helpers.cuh"
 #include "avf_internal.h"
 
 namespace avf {
@@ -29,6 +31,7 @@ namespace avf {
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = 64);
 
 namespace {
+using namespace fused;
 
 constexpr int DIM = 256, HEADS = 8, DH = 32;
 constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
@@ -79,38 +82,6 @@ static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
 enum { IO_NCHW_BF16 = 0, IO_ROWS_F32 = 1 };
 constexpr int POS_LD = 64;   // row stride of the channel-major positional table
 
-// Optional phase timing (-DAVF_FUSED_PROF): CTA 0's MMA thread and first worker thread accumulate clock64() deltas per phase.
-#ifdef AVF_FUSED_PROF
-__device__ unsigned long long g_prof[64];
-struct Prof {      // per-thread accumulators (local memory, L1-resident: a mark costs tens of cycles), flushed to g_prof once at the end
-  long long t0;
-  bool on;
-  unsigned acc[64];
-  __device__ __forceinline__ void start(bool enable) {
-    on = enable;
-    for (int i = 0; i < 64; ++i) acc[i] = 0;
-    t0 = clock64();
-  }
-  __device__ __forceinline__ void mark(int idx) {
-    if (on) {
-      const long long t1 = clock64();
-      acc[idx] += unsigned(t1 - t0);
-      t0 = t1;
-    }
-  }
-  __device__ __forceinline__ void count(int idx) { if (on) acc[idx] += 1; }
-  __device__ __forceinline__ void flush(int lo, int hi) {
-    if (on) for (int i = lo; i < hi; ++i) g_prof[i] += acc[i];
-  }
-};
-#else
-struct Prof {
-  __device__ __forceinline__ void start(bool) {}
-  __device__ __forceinline__ void mark(int) {}
-  __device__ __forceinline__ void count(int) {}
-  __device__ __forceinline__ void flush(int, int) {}
-};
-#endif
 // worker phases
 enum { PW_INPUT = 0, PW_VEC, PW_LN1, PW_WAIT_D1, PW_E1, PW_WAIT_O, PW_E3, PW_WAIT_S, PW_E2, PW_WAIT_X1, PW_LN2, PW_WAIT_HACC, PW_GELU, PW_WAIT_X2,
        PW_OUTPUT, PW_TILES, PW_E2_LD, PW_E2_EXP, PW_E2_XCH, PW_E2_ST,
@@ -141,124 +112,6 @@ struct FusedArgs {
 // bug) before it traps — the trap poisons the context, but pinned host memory stays readable: {block, thread, barrier index,
 // parity}.  Set with avf_debug_set_trap_buffer (tools/trap_probe.py).
 __device__ unsigned* g_trap_buffer = nullptr;
-
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fast_tanh(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// tanh-GELU (models/heads.py:164-166) as 0.5x(1+tanh(x(c0 + c1 x^2))): 6 instructions per element
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float u = x * fmaf(x * x, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, fast_tanh(u), hx);
-}
-// Packed bf16x2 arithmetic for the two MUFU-heavy epilogues (softmax exponentials, tanh-GELU).  Their results are rounded to
-// bf16 anyway (P and gelu(h) are tensor-core operands), so evaluating the transcendental on a bf16 pair halves the MUFU work
-// (16 results / clk / SM -> 32) and the surrounding multiply-adds.  -DAVF_FUSED_PACKED=0 restores the fp32 evaluation.
-#ifndef AVF_FUSED_PACKED
-#define AVF_FUSED_PACKED 1
-#endif
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t r;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
-  return r;
-}
-__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
-  uint32_t r;
-  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(x));
-  return r;
-}
-__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-__device__ __forceinline__ uint32_t fma_bf16x2(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t r;
-  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
-  return r;
-}
-// tanh-GELU of a bf16 pair: 0.5x(1 + tanh(x(c0 + c1 x^2))), 5 packed multiply-adds + 1 MUFU
-__device__ __forceinline__ uint32_t gelu_bf16x2(uint32_t x) {
-  constexpr uint32_t C0 = 0x3F4C3F4Cu;      // 0.796875  ~ sqrt(2/pi)
-  constexpr uint32_t C1 = 0x3D123D12u;      // 0.035645  ~ sqrt(2/pi) * 0.044715
-  constexpr uint32_t HALF = 0x3F003F00u;
-  const uint32_t x2 = mul_bf16x2(x, x);
-  const uint32_t u = mul_bf16x2(x, fma_bf16x2(x2, C1, C0));
-  const uint32_t hx = mul_bf16x2(x, HALF);
-  return fma_bf16x2(hx, tanh_bf16x2(u), hx);
-}
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(0u)
-               : "memory");
-}
-// zero the TMEM columns [lo, hi) of this warp's lanes (lo, hi multiples of 4; warp-uniform; empty when hi <= lo)
-__device__ __forceinline__ void zero_p_columns(uint32_t taddr, int lo, int hi) {
-  int c = lo;
-  for (; c + 16 <= hi; c += 16) tmem_st16_zero(taddr + c);
-  for (; c + 4 <= hi; c += 4) tmem_st4(taddr + c, 0u, 0u, 0u, 0u);
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t desc_sw64(uint32_t addr) { return make_desc(addr, 16, 512, 4); }
-
-__device__ __forceinline__ uint4 pack8(const float* x) {
-  uint4 pk;
-  pk.x = pack_bf16x2(x[0], x[1]);
-  pk.y = pack_bf16x2(x[2], x[3]);
-  pk.z = pack_bf16x2(x[4], x[5]);
-  pk.w = pack_bf16x2(x[6], x[7]);
-  return pk;
-}
-__device__ __forceinline__ uint4 pack8u(const uint32_t* r) {
-  uint4 pk;
-  pk.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));
-  pk.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
-  pk.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));
-  pk.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
-  return pk;
-}
 
 // ---------------------------------------------------------------------------------------------
 // row workers: thread (row, g) owns columns [g*CW, g*CW+CW) of token row `row` (= TMEM lane), CW = 256 / NSPLIT
@@ -398,7 +251,56 @@ struct Worker {
   }
 };
 
-template <int IO>
+// Softmax of one head for a thread that owns NC whole 8-column chunks of its row's window, geometry known at compile time
+// (TAILV > 0: only the first TAILV columns of the last chunk exist).  S is read at `ts`, P (bf16 pairs) written at `tp`;
+// returns the thread's partial row sum.  Same arithmetic as the general path in worker_main.
+template <int NC, int TAILV>
+__device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t tp, float sm_scale, Prof& pf) {
+  float s[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) tmem_ld8(ts + c * 8, reinterpret_cast<uint32_t(&)[8]>(s[c]));
+  tmem_ld_wait();
+  pf.mark(PW_E2_LD);
+  float mloc = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int nv = (TAILV > 0 && c == NC - 1) ? TAILV : 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nv) mloc = fmaxf(mloc, s[c][j]);
+  }
+  pf.mark(PW_E2_EXP);
+  const float mrow = w.exchange_max(mloc);      // also orders every S load of the row before any P store (P overwrites S)
+  pf.mark(PW_E2_XCH);
+  const float nml = -mrow * sm_scale;
+  float sum_g = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int nv = (TAILV > 0 && c == NC - 1) ? TAILV : 8;
+    uint32_t e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (2 * j + 1 < nv) {
+        e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), fmaf(s[c][2 * j + 1], sm_scale, nml)));
+        sum_g += __uint_as_float(e[j] << 16) + __uint_as_float(e[j] & 0xFFFF0000u);
+      } else if (2 * j < nv) {                   // only the low half of the pair exists
+        e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), -INFINITY)) & 0xFFFFu;
+        sum_g += __uint_as_float(e[j] << 16);
+      } else {
+        e[j] = 0u;
+      }
+    }
+    tmem_st4(tp + c * 4, e[0], e[1], e[2], e[3]);
+  }
+  return sum_g;
+}
+
+__host__ __device__ constexpr int slot_of(int n_tok) { return n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : 64); }
+__host__ __device__ constexpr int log2_of(int v) { return v == 16 ? 4 : (v == 32 ? 5 : 6); }
+
+// NTOK > 0: the sequence length is a compile-time constant (the SFormer's 49): the transposing tile sweeps address the staged
+// NCHW frames with immediate offsets and the softmax geometry folds away.  NTOK = 0: everything from FusedArgs.
+template <int IO, int NTOK>
 __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint32_t tmem) {
   Worker w;
   w.smem = smem;
@@ -414,12 +316,13 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
   const int q = w.q, g = w.g, row = w.row;
   const uint32_t tl = w.tl;
   const float* vec = w.vec;
-  const int n_tok = a.n_tok, slot = a.slot, spt = a.spt;
-  const int seq_in_tile = row >> a.slot_log2, t_in_seq = row & (slot - 1);
+  const int n_tok = NTOK ? NTOK : a.n_tok, slot = NTOK ? slot_of(NTOK) : a.slot, spt = NTOK ? 128 / slot_of(NTOK) : a.spt;
+  const int slot_log2 = NTOK ? log2_of(slot_of(NTOK)) : a.slot_log2;
+  const int seq_in_tile = row >> slot_log2, t_in_seq = row & (slot - 1);
   // softmax geometry.  This row attends to score columns [lo, lo + n_tok).  The warp's rows cover sequences s0..s1, so
   // the warp sweeps the 8-column chunks [c_lo, c_hi) and the row's threads split them evenly (<= 8 / NSPLIT chunks each).
   const int lo = seq_in_tile * slot, hi = lo + n_tok;
-  const int s0 = (q * 32) >> a.slot_log2, s1 = (q * 32 + 31) >> a.slot_log2;
+  const int s0 = (q * 32) >> slot_log2, s1 = (q * 32 + 31) >> slot_log2;
   const int c_lo = (s0 * slot) >> 3, c_hi = (s1 * slot + n_tok + 7) >> 3;
   constexpr int MAXC = 8 / NSPLIT;
   const int per = (c_hi - c_lo + NSPLIT - 1) / NSPLIT;
@@ -580,6 +483,25 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           mbar_wait(&bars[B_S_FULL], h & 1);
           tc_fence_after();
           pf.mark(PW_WAIT_S);
+          if constexpr (NTOK > 32 && NSPLIT == 2 && AVF_FUSED_PACKED) {
+            // 64-row slots, compile-time window: the row's chunks are [8 seq, 8 seq + NCH_ALL), thread 0 takes the first four, thread 1 the rest
+            constexpr int NCH_ALL = (NTOK + 7) / 8, NC1 = NCH_ALL - 4, TAILV = NTOK & 7;
+            static_assert(NC1 >= 1 && NC1 <= 4, "softmax split");
+            const uint32_t sb = tl + TM_S + uint32_t(seq_in_tile) * 64, pb = tl + TM_S + uint32_t(seq_in_tile) * 32;
+            const float sum_g = g == 0 ? softmax_fixed<4, 0>(w, sb, pb, sm_scale, pf) : softmax_fixed<NC1, TAILV>(w, sb + 32, pb + 16, sm_scale, pf);
+            reinterpret_cast<float*>(smem + OFF_XCH)[(h & 1) * (128 * 4) + row * 4 + 2 + g] = sum_g;
+            // P columns the MMA reads (all 64 = 128 keys) but this row does not own: zeros; thread g takes TMEM columns [32g, 32g + 32)
+            if (g == seq_in_tile) {
+              zero_p_columns(tl + TM_S, 32 * g + NCH_ALL * 4, 32 * g + 32);
+            } else {
+              tmem_st16_zero(tl + TM_S + 32 * g);
+              tmem_st16_zero(tl + TM_S + 32 * g + 16);
+            }
+            tmem_st_wait();
+            pf.mark(PW_E2_ST);
+            w.arrive_tmem_only(B_P_READY);
+            pf.mark(PW_E2);
+          } else {
           float s[MAXC][8];
 #pragma unroll
           for (int c = 0; c < MAXC; ++c)
@@ -657,6 +579,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           pf.mark(PW_E2_ST);
           w.arrive_tmem_only(B_P_READY);
           pf.mark(PW_E2);
+          }
         }
       }
 
@@ -999,7 +922,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   pf.flush(32, 64);
 }
 
-template <int IO>
+template <int IO, int NTOK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __grid_constant__ FusedArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1042,7 +965,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
   } else if (warp == 2) {
     if (lane == 0) qkv_producer_main<IO>(a, smem, bars);
   } else {
-    worker_main<IO>(a, smem, bars, tmem);
+    worker_main<IO, NTOK>(a, smem, bars, tmem);
   }
 
   tc_fence_before();
@@ -1056,6 +979,15 @@ __global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restr
   pdl_trigger();
   const int c = blockIdx.x * 4 + (threadIdx.x & 3), t = threadIdx.x >> 2;
   pos_t[(blockIdx.x * POS_LD + t) * 4 + (threadIdx.x & 3)] = t < n_tok ? pos[t * DIM + c] : 0.f;
+}
+
+bool fixed_ntok_enabled() {      // developer A/B: AVF_FUSED_FIXED_NTOK=0 keeps the run-time-geometry instantiation for the SFormer too
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AVF_FUSED_FIXED_NTOK");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int sm_count_cached() {
@@ -1100,6 +1032,7 @@ size_t encoder_fused_scratch_bytes() { return size_t(DIM) * POS_LD * sizeof(floa
 
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, void* scratch, cudaStream_t st) {
+  if (fused_variant() != 0 && sformer_fused_supported(s)) return sformer_fused(io_kind, s, L, in, ld_in, out, ld_out, pos, scratch, st);
   AVF_REQUIRE(encoder_fused_supported(s), AVF_EUNSUPPORTED, "fused encoder: unsupported shape dim=%d heads=%d dh=%d mlp=%d n_tok=%d depth=%d",
               s->dim, s->heads, s->dim_head, s->mlp_dim, s->n_tok, s->depth);
   AVF_REQUIRE(io_kind == IO_ROWS_F32 || (pos != nullptr && scratch != nullptr), AVF_EINVAL,
@@ -1131,16 +1064,19 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
   }
   static bool configured = false;
   if (!configured) {
-    AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_NCHW_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_ROWS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_NCHW_BF16, 49>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_NCHW_BF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+    AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_ROWS_F32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     configured = true;
   }
   const int cap = sm_cap();
   const int grid = min(a.n_tiles, cap > 0 ? min(cap, sm_count_cached()) : sm_count_cached());
-  if (io_kind == IO_NCHW_BF16)
-    launch_pdl(encoder_fused_kernel<IO_NCHW_BF16>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
+  if (io_kind == IO_NCHW_BF16 && a.n_tok == 49 && NSPLIT == 2 && fixed_ntok_enabled())     // the SFormer's 7 x 7 maps: compile-time geometry
+    launch_pdl(encoder_fused_kernel<IO_NCHW_BF16, 49>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
+  else if (io_kind == IO_NCHW_BF16)
+    launch_pdl(encoder_fused_kernel<IO_NCHW_BF16, 0>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
   else
-    launch_pdl(encoder_fused_kernel<IO_ROWS_F32>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
+    launch_pdl(encoder_fused_kernel<IO_ROWS_F32, 0>, grid, NUM_THREADS, SMEM_ALLOC, st, a);
   AVF_LAUNCH_CHECK("encoder_fused_kernel");
   return 0;
 }

@@ -1,0 +1,121 @@
+"""Parity at the BENCHMARKED sizes (bench.py: 512 clips x 16 frames per GPU): 8192 stage-3 maps through the persistent fused SFormer
+kernel (4096 tiles, 28 per CTA: every ring and mbarrier phase bit wraps many times) and 512 x 17 tokens through avf_tformer_fwd.
+The CPU oracle is too slow for all of it, so a sample of frames / clips spread over the first, middle and last tiles of several
+CTAs is checked against the fp64 oracle, and the WHOLE output is pinned by a size-independent property: a tile's result does not
+depend on where in the launch it is computed, so the full run must equal the same frames run in small launches, bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+import avformer_b200 as A
+from oracle import avformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+AF = A.functional
+
+N_CLIPS, T = 512, 16
+BF16_ATOL = 2e-2          # north_star: logits within 2e-2 absolute in BF16
+
+
+def _maxerr(a, b):
+    return (a.double().cpu() - b.double().cpu()).abs().max().item()
+
+
+def _model(seed, precision="bf16"):
+    m = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU").set_clip_length(T)
+    m.load_state_dict(O.make_state_dict(seed, T), strict=True)
+    return m.cuda().eval().set_precision(precision)
+
+
+def _bench_inputs(seed):
+    """bench.py's synthetic batch (same distributions and shapes)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    stage3 = torch.clamp(torch.randn(N_CLIPS * T, 256, 7, 7, generator=g) * 1.7 + 0.6, min=0).bfloat16()
+    frame = (torch.randn(N_CLIPS * T, 512, generator=g).abs() * 1.2).bfloat16()
+    audio = torch.randn(N_CLIPS, 512, generator=g).abs()
+    return stage3, frame, audio
+
+
+def _sample_frames(n_frames, n_cta=148):
+    """Frames of the first, a middle and the last tile of CTAs 0, 1, 73, 146, 147 (static striding: CTA b takes tiles b, b + grid, ...)
+    plus the very last frames and a few random ones: 64 in total."""
+    n_tiles = n_frames // 2
+    per = (n_tiles + n_cta - 1) // n_cta
+    tiles = set()
+    for b in (0, 1, 73, 146, 147):
+        for k in (0, per // 2, per - 1, per - 2):
+            t = b + k * n_cta
+            if 0 <= t < n_tiles:
+                tiles.add(t)
+    tiles.update((n_tiles - 1, n_tiles - 2))
+    frames = sorted({2 * t + j for t in tiles for j in (0, 1)})
+    rng = np.random.default_rng(0)
+    extra = [int(f) for f in rng.choice(n_frames, size=max(0, 64 - len(frames)), replace=False)]
+    return torch.tensor(sorted(set(frames + extra))[:64])
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_sformer_8192_frames_sampled_oracle_and_launch_position_independence(variant):
+    seed = 4242
+    stage3, _, _ = _bench_inputs(seed)
+    m = _model(seed)
+    sf = m.video_model.video_model.s_former
+    L = A._lib.lib()
+    prev = L.avf_set_fused_variant(variant)
+    try:
+        with torch.no_grad():
+            x = stage3.cuda()
+            full = sf.sformer(x)
+            again = sf.sformer(x)
+            assert torch.equal(full, again)                                   # run-to-run bit reproducibility at 28 tiles per CTA
+            # the same frames in launches of 296 frames (2 tiles per CTA at most) and of 2 frames (one tile, one CTA)
+            for lo in (0, 296 * 5, 296 * 13, 8192 - 296):
+                part = sf.sformer(x[lo:lo + 296].contiguous())
+                assert torch.equal(part, full[lo:lo + 296]), f"frames {lo}..{lo + 296} differ between the full and the small launch"
+            idx = _sample_frames(stage3.shape[0])
+            for f in idx[::8].tolist():
+                f2 = f - (f % 2)
+                one = sf.sformer(x[f2:f2 + 2].contiguous())
+                assert torch.equal(one, full[f2:f2 + 2])
+        p = O.cast_params(O.make_state_dict(seed, T, hot_path_only=True), torch.float64)
+        ref = O.sformer_tokens(stage3[idx].double(), p, "video_model.video_model.s_former.")
+        got = full[idx.cuda()]
+        d = (got.double().cpu() - ref).abs()
+        assert d.max().item() < 0.2 and d.mean().item() < 2e-2, f"max {d.max().item():.3e} mean {d.mean().item():.3e}"
+        assert torch.isfinite(full.float()).all()
+    finally:
+        L.avf_set_fused_variant(prev)
+
+
+def test_tformer_and_heads_512_clips_sampled_oracle():
+    """512 x 17 tokens through avf_tformer_fwd, then both AU_formers and the fusion head, at the bench batch; 64 clips spread over
+    the batch against the fp64 oracle (logits 2e-2, decisions identical where the reference logit is not within 2e-2 of 0), and the
+    whole batch against the same clips run in batches of 64."""
+    seed = 4343
+    _, frame, audio = _bench_inputs(seed)
+    m = _model(seed)
+    vm = m.video_model.video_model
+
+    def chain(fr, au):
+        cls = vm.t_former(fr)
+        _, vt = m.video_model.au_head(cls)
+        _, at = m.audio_model.au_head(au)
+        return cls, m.au_head(torch.cat([at, vt], 2))
+
+    with torch.no_grad():
+        cls_full, logits_full = chain(frame.cuda(), audio.cuda())
+        for lo in (0, 192, 448):
+            cls_part, logits_part = chain(frame[lo * T:(lo + 64) * T].cuda(), audio[lo:lo + 64].cuda())
+            assert _maxerr(cls_part, cls_full[lo:lo + 64]) < 1e-5 and _maxerr(logits_part, logits_full[lo:lo + 64]) < 1e-5
+    idx = torch.cat([torch.arange(0, 16), torch.arange(248, 264), torch.arange(496, 512), torch.tensor([31, 63, 64, 127, 128, 200, 255, 256, 300, 383, 384, 400, 447, 448, 470, 495])])
+    fsel = (idx[:, None] * T + torch.arange(T)).reshape(-1)
+    p = O.cast_params(O.make_state_dict(seed, T, hot_path_only=True), torch.float64)
+    cls_ref = O.tformer(frame[fsel].double(), p, "video_model.video_model.t_former.", T)
+    assert _maxerr(cls_full[idx.cuda()], cls_ref) < 0.15
+    _, vt = O.au_former(cls_ref, p, "video_model.au_head.")
+    _, at = O.au_former(audio[idx].double(), p, "audio_model.au_head.")
+    ref_logits = O.fusion_head(torch.cat([at, vt], 2), p, "au_head.")
+    got = logits_full[idx.cuda()].double().cpu()
+    assert (got - ref_logits).abs().max().item() < BF16_ATOL
+    sure = ref_logits.abs() > BF16_ATOL
+    assert bool((((got > 0) == (ref_logits > 0)) | ~sure).all())
