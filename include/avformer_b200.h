@@ -85,10 +85,6 @@ int         avf_device_info(int32_t* sm_count, int32_t* cc, int32_t* has_tcgen05
  * kernel-per-operation path instead (used by the A/B parity tests); returns the previous setting. */
 int         avf_set_fused_enabled(int enabled);
 int         avf_encoder_fused_supported(const avf_stack_shape* s, int mode);
-/* Which generation of the fused kernel takes the stacks with 33..64 tokens per sequence (the SFormer): 1 (default) =
- * csrc/avf_sformer_fused.cu (16 row-worker warps, two interleaved head chains on compact score tiles), 0 = the general kernel
- * of csrc/avf_layer_fused.cu for every shape (A/B tests).  Returns the previous setting. */
-int         avf_set_fused_variant(int variant);
 /* Upper bound on the grid of the persistent kernels (fused encoder, tcgen05 GEMM) launched AFTER the call; 0 = all SMs.
  * Returns the previous value.  Lets a caller run two kernel chains side by side on disjoint SM sets (each persistent CTA
  * owns a whole SM): e.g. cap 116 around the SFormer launch, cap 32 around the TFormer / head chain on another stream. */

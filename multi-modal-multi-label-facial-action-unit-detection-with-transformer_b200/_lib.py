@@ -55,7 +55,6 @@ SIGNATURES = {
     "avf_launch_count": (ctypes.c_uint64, []),
     "avf_device_info": (ctypes.c_int, [ctypes.POINTER(_i32)] * 3),
     "avf_set_fused_enabled": (ctypes.c_int, [ctypes.c_int]),
-    "avf_set_fused_variant": (ctypes.c_int, [ctypes.c_int]),
     "avf_encoder_fused_supported": (ctypes.c_int, [ctypes.POINTER(StackShape), ctypes.c_int]),
     "avf_debug_fused_prof": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]),
     "avf_encoder_workspace_bytes": (_sz, [ctypes.POINTER(StackShape), ctypes.c_int]),
@@ -171,8 +170,6 @@ def lib() -> ctypes.CDLL:
                 fn.restype, fn.argtypes = res, args
             if os.environ.get("AVF_PDL", "") in ("0", "off"):
                 handle.avf_set_pdl_enabled(0)
-            if os.environ.get("AVF_FUSED_VARIANT", "") in ("0", "1"):      # developer A/B of the two fused-kernel generations
-                handle.avf_set_fused_variant(int(os.environ["AVF_FUSED_VARIANT"]))
             if handle.avf_abi_version() != 1:
                 raise RuntimeError("avformer_b200: ABI version mismatch")
             _lib = handle

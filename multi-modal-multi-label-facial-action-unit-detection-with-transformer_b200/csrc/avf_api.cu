@@ -17,8 +17,6 @@ bool pdl_enabled() { return g_pdl.load() != 0; }
 static std::atomic<int> g_sm_cap{0};     // avf_set_sm_cap
 int sm_cap() { return g_sm_cap.load(); }
 static std::atomic<int> g_fused{1};      // avf_set_fused_enabled: 0 forces the kernel-per-op path (A/B tests)
-static std::atomic<int> g_fused_variant{1};   // avf_set_fused_variant
-int fused_variant() { return g_fused_variant.load(); }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -155,8 +153,6 @@ int avf_set_fused_enabled(int enabled) {
   return old;
 }
 
-int avf_set_fused_variant(int variant) { return g_fused_variant.exchange(variant != 0 ? 1 : 0); }
-
 int avf_set_pdl_enabled(int enabled) { return g_pdl.exchange(enabled ? 1 : 0); }
 
 int avf_set_sm_cap(int cap) { return g_sm_cap.exchange(cap > 0 ? cap : 0); }
@@ -166,10 +162,7 @@ int avf_encoder_fused_supported(const avf_stack_shape* s, int mode) {
 }
 
 /* Debug: per-phase cycle counters of the fused encoder kernel (library built with -DAVF_FUSED_PROF); else AVF_EUNSUPPORTED. */
-int avf_debug_fused_prof(uint64_t* out64, int reset) {
-  unsigned long long* o = reinterpret_cast<unsigned long long*>(out64);
-  return fused_variant() != 0 ? sformer_fused_prof_read(o, reset) : fused_prof_read(o, reset);
-}
+int avf_debug_fused_prof(uint64_t* out64, int reset) { return fused_prof_read(reinterpret_cast<unsigned long long*>(out64), reset); }
 
 int avf_debug_gemm_prof(uint64_t* out16) { return gemm_prof_read(reinterpret_cast<unsigned long long*>(out16)); }
 

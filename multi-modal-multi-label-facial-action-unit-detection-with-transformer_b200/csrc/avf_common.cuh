@@ -170,6 +170,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (mbarrier.try_wait may suspend the thread for a system-dependent time before it answers "not yet").
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // The same with a suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the hint expires, so a
 // waiting warp issues (almost) no instructions and leaves its scheduler's issue slots to the warps that have work.
 #ifndef AVF_SPIN_HINT_NS

@@ -67,13 +67,6 @@ size_t encoder_fused_scratch_bytes();                        // scratch of the N
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, void* scratch, cudaStream_t st);
 
-// avf_sformer_fused.cu: the same stack family for sequences of 33..64 tokens (the SFormer), two head chains on 16 worker warps
-int fused_variant();                                         // avf_set_fused_variant (avf_api.cu)
-bool sformer_fused_supported(const avf_stack_shape* s);
-int sformer_fused_prof_read(unsigned long long* out64, int reset);
-int sformer_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
-                  const float* pos, void* scratch, cudaStream_t st);
-
 // avf_gemm_umma.cu
 int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, int ldw, const float* bias, const float* res, int ld_res,
               const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, void* ws, size_t ws_bytes,

@@ -33,36 +33,51 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 namespace {
 using namespace fused;
 
+// How the weight producer waits (it serves two things at once: ring slots and the next tile's input frames):
+// 0 = mbarrier.try_wait on both (each probe may suspend the thread for the hardware's time limit), 1 = non-blocking test_wait on
+// both (pure spin), 2 = try_wait on the ring slot, test_wait on the input-buffer probe.
+#ifndef AVF_PROD_POLL
+#define AVF_PROD_POLL 2
+#endif
+
 constexpr int DIM = 256, HEADS = 8, DH = 32;
 constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
 #ifndef AVF_FUSED_NSPLIT
 #define AVF_FUSED_NSPLIT 2
 #endif
 constexpr int NSPLIT = AVF_FUSED_NSPLIT;   // threads per token row (each owns DIM / NSPLIT columns of the residual stream)
-static_assert(NSPLIT == 2 || NSPLIT == 4, "NSPLIT");
+static_assert(NSPLIT == 2, "two threads per token row (the packed softmax exchanges a pair)");
 constexpr int WORKER_T0 = 96;              // first worker thread
 constexpr int NUM_WORKERS = 128 * NSPLIT;
 constexpr int NUM_THREADS = WORKER_T0 + NUM_WORKERS;
-// Main weight ring, 16 KB slots.  Slots 2-4 are free in every phase (out-projection slices rotate over them); the MLP weights
-// rotate over all nine: slots 0-1 alias the Q/K/V staging and slots 5-8 the 64 KB of A1 (O staging + QKV ring), all idle in the
-// MLP phase — 144 KB in flight cover the L2 latency at the MLP's consumption rate (16 KB per 256 tensor cycles).
-constexpr int RING = 9, RING_LO = 2, RING_HI = 5, SLOT_BYTES = 16384;
-constexpr int QRING = 4, QSLOT_BYTES = 12288;   // QKV ring: one slot = one 64-wide K panel of [Wq_h; Wk_h; Wv_h] (3 x 32 rows x 128 B)
+// Main weight ring, 16 KB slots laid out contiguously from OFF_Q.  Slots 2-3 are free in every phase (out-projection slices
+// rotate over them); the MLP weights rotate over all nine: slots 0-1 alias the Q/K/V staging and slots 4-8 the O staging + QKV
+// ring, all idle in the MLP phase — 144 KB in flight cover the L2 latency at the MLP's consumption rate (16 KB per 256 tensor cycles).
+constexpr int RING = 9, RING_LO = 2, RING_HI = 4, SLOT_BYTES = 16384;
+// QKV ring: one slot = one 64-wide K panel of [Wq_h; Wk_h; Wv_h] (3 x 32 rows x 128 B); six slots = one and a half heads in
+// flight.  With four (one head) every QKV_{h+1} waited ~400 cycles for its first panels, and the chain E1_h -> QKV_{h+1} -> E1_{h+1}
+// (D1 is single-buffered in TMEM) is what paces the attention phase.
+#ifndef AVF_QRING
+#define AVF_QRING 6
+#endif
+constexpr int QRING = AVF_QRING, QSLOT_BYTES = 12288;
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int OFF_A0 = 0;                          // 64 KB  LN output [128 x 256] bf16, 4 K-panels; also the NCHW input staging
-constexpr int OFF_A1 = 65536;                      // 64 KB  O_h staging + QKV ring (both ahead of the attention phase); NCHW output staging
-constexpr int OFF_OST = OFF_A1;                    //   2 x 8 KB  O_h / l  [128 x 32] K-major SW64, double buffered
-constexpr int OFF_QRING = OFF_A1 + 16384;          //   4 x 12 KB QKV weight ring
-constexpr int OFF_Q = 131072;                      // 8 KB   Q_h [128 x 32] K-major SW64
+constexpr int OFF_Q = 65536;                       // 8 KB   Q_h [128 x 32] K-major SW64
 constexpr int OFF_K = OFF_Q + 8192;                // 8 KB   K_h
 constexpr int OFF_V = OFF_K + 8192;                // 2x8 KB V_h [128 tok x 32] MN-major SW64, double buffered
-constexpr int OFF_RING = OFF_V + 16384;            // 3 x 16 KB weight ring (slots 2-4; slots 0-1 = the 32 KB of Q/K/V staging above)
+constexpr int OFF_RING = OFF_V + 16384;            // 2 x 16 KB weight ring (slots 2-3; slots 0-1 = the 32 KB of Q/K/V staging above)
+constexpr int OFF_OST = OFF_RING + (RING_HI - RING_LO) * SLOT_BYTES;   // 8 KB  O_h / l  [128 x 32] K-major SW64 (single: out-proj(h-1) is issued before PV(h))
+constexpr int OFF_QRING = OFF_OST + 8192;          // QRING x 12 KB QKV weight ring; also the NCHW output staging (2 x 64 x 256 bf16 at most)
+constexpr int OFF_OUTST = OFF_QRING;
+static_assert(QRING * QSLOT_BYTES >= 2 * 64 * 256 * 2, "the NCHW output staging lives in the QKV ring");
+constexpr int OFF_XCH = OFF_QRING + QRING * QSLOT_BYTES;               // row exchange [2][128][4] floats
+static_assert(OFF_XCH - OFF_Q == RING * SLOT_BYTES, "the nine MLP ring slots tile [OFF_Q, OFF_XCH) exactly");
 static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguous from OFF_Q");
-constexpr int OFF_XCH = OFF_RING + (RING_HI - RING_LO) * SLOT_BYTES;
-__host__ __device__ constexpr int slot_offset(uint32_t s) { return s < RING_HI ? OFF_Q + int(s) * SLOT_BYTES : OFF_A1 + int(s - RING_HI) * SLOT_BYTES; }   // row exchange [2][128][4] floats
-constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors (LN affine, biases), fp32
-constexpr int V_LN1G = 0, V_LN1B = 256, V_BOUT = 512, V_LN2G = 768, V_LN2B = 1024, V_BFF2 = 1280, V_BFF1 = 1536;
+__host__ __device__ constexpr int slot_offset(uint32_t s) { return OFF_Q + int(s) * SLOT_BYTES; }
+constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors
+constexpr int V_BOUT = 0, V_BFF2 = 256, V_BFF1 = 512;   // fp32 biases
 constexpr int V_B16 = V_BFF1 + MAX_MLP;             // then bf16 copies of the LayerNorm affine vectors: [ln1_g | ln1_b | ln2_g | ln2_b] x 256
 constexpr int OFF_BAR = OFF_VEC + (V_B16 + 512) * 4;
 constexpr int SMEM_USED = OFF_BAR + 512;
@@ -86,7 +101,8 @@ constexpr int POS_LD = 64;   // row stride of the channel-major positional table
 enum { PW_INPUT = 0, PW_VEC, PW_LN1, PW_WAIT_D1, PW_E1, PW_WAIT_O, PW_E3, PW_WAIT_S, PW_E2, PW_WAIT_X1, PW_LN2, PW_WAIT_HACC, PW_GELU, PW_WAIT_X2,
        PW_OUTPUT, PW_TILES, PW_E2_LD, PW_E2_EXP, PW_E2_XCH, PW_E2_ST,
        // MMA thread phases
-       PM_WAIT_A0 = 32, PM_QKV, PM_WAIT_STAGED, PM_S, PM_WAIT_P, PM_PV, PM_WAIT_OD7, PM_OUT, PM_WAIT_A0B, PM_FF1, PM_WAIT_H, PM_FF2, PM_RINGWAIT };
+       PM_WAIT_A0 = 32, PM_QKV, PM_WAIT_STAGED, PM_S, PM_WAIT_P, PM_PV, PM_WAIT_OD7, PM_OUT, PM_WAIT_A0B, PM_FF1, PM_WAIT_H, PM_FF2, PM_RINGWAIT,
+       PM_RW_QKV, PM_RW_OUT, PM_RW_FF1, PM_RW_FF2, PM_REFILL_CYC, PM_REFILL_N };
 
 struct LayerArgs {
   CUtensorMap tm_qkv, tm_out, tm_w1, tm_w2;     // tm_out: box [256 rows x 32 cols], 64B swizzle (one head's K slice of Wout)
@@ -202,7 +218,8 @@ struct Worker {
     finish_stats(st, mean, rstd);
   }
   // Sweep 2: LN(x) -> A0 (bf16, K-major SW128 panels), x + next_bias -> TMEM; then signal the MMA thread.
-  __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, int v_gamma, int v_beta, int v_next_bias) {
+  // (x - mean) * rstd in fp32, the affine part on bf16 pairs (gamma / beta pre-rounded to bf16 in shared memory); ln_sel 0 / 1 = LN1 / LN2
+  __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, int ln_sel, int v_next_bias) {
     const int cbase = g * CW;
     const float nmr = -mean * rstd;
 #pragma unroll 1
@@ -215,9 +232,7 @@ struct Worker {
       const int chunk0 = (col0 & 63) >> 3;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-#if AVF_FUSED_PACKED
-        // (x - mean) * rstd in fp32, the affine part on bf16 pairs (gamma / beta pre-rounded to bf16 in shared memory)
-        const __nv_bfloat16* v16 = reinterpret_cast<const __nv_bfloat16*>(vec + V_B16) + (v_gamma == V_LN1G ? 0 : 512) + col0 + ch * 8;
+        const __nv_bfloat16* v16 = reinterpret_cast<const __nv_bfloat16*>(vec + V_B16) + ln_sel * 512 + col0 + ch * 8;
         const uint4 gm = *reinterpret_cast<const uint4*>(v16), bt = *reinterpret_cast<const uint4*>(v16 + 256);
         uint4 pk;
         pk.x = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8], rstd, nmr), fmaf(x[ch * 8 + 1], rstd, nmr)), gm.x, bt.x);
@@ -225,19 +240,6 @@ struct Worker {
         pk.z = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 4], rstd, nmr), fmaf(x[ch * 8 + 5], rstd, nmr)), gm.z, bt.z);
         pk.w = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 6], rstd, nmr), fmaf(x[ch * 8 + 7], rstd, nmr)), gm.w, bt.w);
         *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pk;
-#else
-        float y[8];
-#pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 gm = *reinterpret_cast<const float4*>(vec + v_gamma + col0 + ch * 8 + j);
-          const float4 bt = *reinterpret_cast<const float4*>(vec + v_beta + col0 + ch * 8 + j);
-          y[j] = fmaf(fmaf(x[ch * 8 + j], rstd, nmr), gm.x, bt.x);
-          y[j + 1] = fmaf(fmaf(x[ch * 8 + j + 1], rstd, nmr), gm.y, bt.y);
-          y[j + 2] = fmaf(fmaf(x[ch * 8 + j + 2], rstd, nmr), gm.z, bt.z);
-          y[j + 3] = fmaf(fmaf(x[ch * 8 + j + 3], rstd, nmr), gm.w, bt.w);
-        }
-        *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pack8(y);
-#endif
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -261,19 +263,26 @@ __device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t 
   for (int c = 0; c < NC; ++c) tmem_ld8(ts + c * 8, reinterpret_cast<uint32_t(&)[8]>(s[c]));
   tmem_ld_wait();
   pf.mark(PW_E2_LD);
-  float mloc = -INFINITY;
+  float mc[NC];                                   // per-chunk maxima as trees (independent chains), then one short chain across chunks
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    const int nv = (TAILV > 0 && c == NC - 1) ? TAILV : 8;
+    if (TAILV > 0 && c == NC - 1) {
+      mc[c] = s[c][0];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (j < nv) mloc = fmaxf(mloc, s[c][j]);
+      for (int j = 1; j < 8; ++j)
+        if (j < TAILV) mc[c] = fmaxf(mc[c], s[c][j]);
+    } else {
+      mc[c] = fmaxf(fmaxf(fmaxf(s[c][0], s[c][1]), fmaxf(s[c][2], s[c][3])), fmaxf(fmaxf(s[c][4], s[c][5]), fmaxf(s[c][6], s[c][7])));
+    }
   }
+  float mloc = mc[0];
+#pragma unroll
+  for (int c = 1; c < NC; ++c) mloc = fmaxf(mloc, mc[c]);
   pf.mark(PW_E2_EXP);
   const float mrow = w.exchange_max(mloc);      // also orders every S load of the row before any P store (P overwrites S)
   pf.mark(PW_E2_XCH);
   const float nml = -mrow * sm_scale;
-  float sum_g = 0.f;
+  float sum_lo = 0.f, sum_hi = 0.f;              // low / high halves of the pairs: two independent chains
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int nv = (TAILV > 0 && c == NC - 1) ? TAILV : 8;
@@ -282,17 +291,18 @@ __device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t 
     for (int j = 0; j < 4; ++j) {
       if (2 * j + 1 < nv) {
         e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), fmaf(s[c][2 * j + 1], sm_scale, nml)));
-        sum_g += __uint_as_float(e[j] << 16) + __uint_as_float(e[j] & 0xFFFF0000u);
+        sum_lo += __uint_as_float(e[j] << 16);
+        sum_hi += __uint_as_float(e[j] & 0xFFFF0000u);
       } else if (2 * j < nv) {                   // only the low half of the pair exists
         e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), -INFINITY)) & 0xFFFFu;
-        sum_g += __uint_as_float(e[j] << 16);
+        sum_lo += __uint_as_float(e[j] << 16);
       } else {
         e[j] = 0u;
       }
     }
     tmem_st4(tp + c * 4, e[0], e[1], e[2], e[3]);
   }
-  return sum_g;
+  return sum_lo + sum_hi;
 }
 
 __host__ __device__ constexpr int slot_of(int n_tok) { return n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : 64); }
@@ -361,7 +371,11 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           // shared-memory reads of the staged frame overlap their L1/L2 round trip
           float4 p[8];
 #pragma unroll
+#ifdef AVF_EXP_POS_HOT      // timing experiment only (wrong results): every block reads the first block's positional values -> L1 hits
+          for (int j = 0; j < 8; ++j) p[j] = __ldg(ppt + j * POS_LD);
+#else
           for (int j = 0; j < 8; ++j) p[j] = __ldg(ppt + (c0 / 4 + j) * POS_LD);
+#endif
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             x[4 * j] = __bfloat162float(src16[(c0 + 4 * j) * n_tok]) + p[j].x;
@@ -410,8 +424,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         if (vec_loaded) bar_sync(5, NUM_WORKERS);  // previous layer's readers are done
         float* vs = reinterpret_cast<float*>(smem + OFF_VEC);
         for (int i = wt; i < DIM; i += NUM_WORKERS) {
-          vs[V_LN1G + i] = L.ln1_g[i]; vs[V_LN1B + i] = L.ln1_b[i]; vs[V_BOUT + i] = L.b_out[i];
-          vs[V_LN2G + i] = L.ln2_g[i]; vs[V_LN2B + i] = L.ln2_b[i]; vs[V_BFF2 + i] = L.b_ff2[i];
+          vs[V_BOUT + i] = L.b_out[i]; vs[V_BFF2 + i] = L.b_ff2[i];
           __nv_bfloat16* v16 = reinterpret_cast<__nv_bfloat16*>(vs + V_B16);
           v16[i] = __float2bfloat16_rn(L.ln1_g[i]); v16[256 + i] = __float2bfloat16_rn(L.ln1_b[i]);
           v16[512 + i] = __float2bfloat16_rn(L.ln2_g[i]); v16[768 + i] = __float2bfloat16_rn(L.ln2_b[i]);
@@ -421,7 +434,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         vec_loaded = true;
       }
       pf.mark(PW_VEC);
-      w.normalize_from_tmem(mean, rstd, V_LN1G, V_LN1B, V_BOUT);
+      w.normalize_from_tmem(mean, rstd, 0, V_BOUT);
       pf.mark(PW_LN1);
 
       // ---- attention: per head  E1 (QKV -> smem), E3 of the previous head (O -> A1), E2 (softmax) -------------
@@ -467,7 +480,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_l) : "f"(sums[0] + sums[1]));
           }
 #endif
-          uint8_t* ob = smem + OFF_OST + ((h - 1) & 1) * 8192 + row * 64;
+          uint8_t* ob = smem + OFF_OST + row * 64;
           const uint32_t sw = uint32_t((row >> 1) & 3);
 #pragma unroll
           for (int c = 0; c < OW / 8; ++c) {
@@ -588,7 +601,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
       tc_fence_after();
       pf.mark(PW_WAIT_X1);
       w.stats_from_tmem(mean, rstd);
-      w.normalize_from_tmem(mean, rstd, V_LN2G, V_LN2B, V_BFF2);
+      w.normalize_from_tmem(mean, rstd, 1, V_BFF2);
       pf.mark(PW_LN2);
 
       // ---- MLP: per 128-column chunk of the hidden layer, bias + tanh-GELU -> bf16 A operand ---------------------
@@ -638,7 +651,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
 
     // ---- tile output ----------------------------------------------------------------------------
     {
-      __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(smem + OFF_A1) + size_t(seq_in_tile * DIM + g * CW) * n_tok + t_in_seq;
+      __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(smem + OFF_OUTST) + size_t(seq_in_tile * DIM + g * CW) * n_tok + t_in_seq;
       float* dst32 = static_cast<float*>(a.out) + grow * a.ld_out + g * CW;
 #pragma unroll 1
       for (int c0 = 0; c0 < CW; c0 += 32) {
@@ -660,7 +673,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
         bar_sync(5, NUM_WORKERS);
         if (threadIdx.x == WORKER_T0) {
           __nv_bfloat16* gdst = static_cast<__nv_bfloat16*>(a.out) + size_t(tile) * spt * n_tok * DIM;
-          bulk_store_1d(gdst, smem + OFF_A1, uint32_t(seqs_here) * n_tok * DIM * 2);   // read completion: see the next tile's input sweep
+          bulk_store_1d(gdst, smem + OFF_OUTST, uint32_t(seqs_here) * n_tok * DIM * 2);   // read completion: see the next tile's input sweep
         }
       }
     }
@@ -689,7 +702,11 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
   auto poll_loader = [&]() {
     if (IO != IO_NCHW_BF16 || load_tile >= a.n_tiles) return;
     if (need_free) {
+#if AVF_PROD_POLL >= 1
+      if (!mbar_test_wait(&bars[B_A0_FREE], n_free & 1)) return;     // a probe that never suspends: this thread has weight slots to serve
+#else
       if (!mbar_try_wait(&bars[B_A0_FREE], n_free & 1)) return;
+#endif
       ++n_free;
     }
     const int seqs_here = min(a.spt, a.n_seq - load_tile * a.spt);
@@ -705,7 +722,11 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
   auto poll_wait = [&](uint64_t* bar, uint32_t parity) {
     poll_loader();
     const long long t0 = clock64();
+#if AVF_PROD_POLL == 1
+    while (!mbar_test_wait(bar, parity)) {
+#else
     while (!mbar_try_wait(bar, parity)) {
+#endif
       poll_loader();
       if (clock64() - t0 > 4000000000LL) {
         unsigned* tb = g_trap_buffer;
@@ -783,7 +804,7 @@ __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* b
 // the issue loop is a handful of instructions per MMA); only the elected lane issues tcgen05.mma / tcgen05.commit.
 __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint32_t tmem) {
   const bool leader = elect_one();
-  const uint32_t a0 = smem_u32(smem + OFF_A0), a1 = smem_u32(smem + OFF_A1);
+  const uint32_t a0 = smem_u32(smem + OFF_A0);
   const uint32_t qs = smem_u32(smem + OFF_Q), ks = smem_u32(smem + OFF_K), vs = smem_u32(smem + OFF_V);
   const uint32_t smem0 = smem_u32(smem), qring = smem_u32(smem + OFF_QRING), ost = smem_u32(smem + OFF_OST);
   const int kmax = 128;                        // S / P span the whole tile: sequences sit in power-of-two row slots
@@ -797,7 +818,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     pf.mark(ring_phase);
     mbar_wait(&bars[B_RING_FULL + s], (cbits >> s) & 1u);
     tc_fence_after();
-    pf.mark(PM_RINGWAIT);
+    pf.mark(ring_phase == PM_OUT ? PM_RW_OUT : (ring_phase == PM_FF1 ? PM_RW_FF1 : PM_RW_FF2));
     return smem0 + uint32_t(slot_offset(s));
   };
   auto slot_release = [&](uint32_t s) {
@@ -810,7 +831,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       pf.mark(ring_phase);
       mbar_wait(&bars[B_QR_FULL + s], ph);
       tc_fence_after();
-      pf.mark(PM_RINGWAIT);
+      pf.mark(PM_RW_QKV);
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(qring + s * QSLOT_BYTES);
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
@@ -821,7 +842,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   };
   auto outproj = [&](int h) {                 // x += (O_h / l) Wout[:, 32h .. 32h+32)^T   (x + b_out was stored by the workers)
     const uint32_t s = RING_LO + h % (RING_HI - RING_LO), sb = slot_wait(s);
-    const uint64_t da = desc_sw64(ost + (h & 1) * 8192), db = desc_sw64(sb);
+    const uint64_t da = desc_sw64(ost), db = desc_sw64(sb);
     if (leader) umma_bf16(tmem + TM_X, da, db, id_256, 1u);
     if (leader) umma_bf16(tmem + TM_X, da + 2, db + 2, id_256, 1u);
     slot_release(s);
@@ -1032,7 +1053,6 @@ size_t encoder_fused_scratch_bytes() { return size_t(DIM) * POS_LD * sizeof(floa
 
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, void* scratch, cudaStream_t st) {
-  if (fused_variant() != 0 && sformer_fused_supported(s)) return sformer_fused(io_kind, s, L, in, ld_in, out, ld_out, pos, scratch, st);
   AVF_REQUIRE(encoder_fused_supported(s), AVF_EUNSUPPORTED, "fused encoder: unsupported shape dim=%d heads=%d dh=%d mlp=%d n_tok=%d depth=%d",
               s->dim, s->heads, s->dim_head, s->mlp_dim, s->n_tok, s->depth);
   AVF_REQUIRE(io_kind == IO_ROWS_F32 || (pos != nullptr && scratch != nullptr), AVF_EINVAL,

@@ -21,7 +21,7 @@ with torch.no_grad():
     L.avf_debug_fused_prof(buf, 0)
 print(f"kernel {e0.elapsed_time(e1)*1e3:.1f} us for {frames} frames")
 W = ["INPUT", "VEC", "LN1", "WAIT_D1", "E1", "WAIT_O", "E3", "WAIT_S", "E2", "WAIT_X1", "LN2", "WAIT_HACC", "GELU", "WAIT_X2", "OUTPUT"]
-M = ["WAIT_A0", "QKV", "WAIT_STAGED", "S", "WAIT_P", "PV", "WAIT_OD7", "OUT", "WAIT_A0B", "FF1", "WAIT_H", "FF2", "RINGWAIT"]
+M = ["WAIT_A0", "QKV", "WAIT_STAGED", "S", "WAIT_P", "PV", "WAIT_OD7", "OUT", "WAIT_A0B", "FF1", "WAIT_H", "FF2", "RINGWAIT", "RINGWAIT_QKV", "RINGWAIT_OUT", "RINGWAIT_FF1", "RINGWAIT_FF2"]
 tiles = max(1, buf[15])
 print(f"CTA 0: {tiles} tiles; cycles per tile")
 tw = sum(buf[i] for i in range(15)); tm = sum(buf[32 + i] for i in range(len(M)))

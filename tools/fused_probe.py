@@ -48,13 +48,8 @@ def head_case(n_clips, seed=5):
 
 
 if __name__ == "__main__":
-    Lh = A._lib.lib()
-    for variant in (1, 0):
-        Lh.avf_set_fused_variant(variant)
-        print(f"--- fused variant {variant}")
-        for f in (2, 1, 7, 300):
-            sformer_case(f)
-    Lh.avf_set_fused_variant(1)
+    for f in (2, 1, 7, 300):
+        sformer_case(f)
     for b in (1, 10, 33, 512):
         head_case(b)
     # timing
@@ -63,9 +58,8 @@ if __name__ == "__main__":
     m.spatial_transformer.precision = "bf16"
     fm = (torch.clamp(torch.randn(8192, 256, 7, 7) * 1.7 + 0.6, min=0)).bfloat16().cuda()
     with torch.no_grad():
-        for en, variant in ((False, 1), (True, 0), (True, 1)):
+        for en in (False, True):
             AF.set_fused_enabled(en)
-            Lh.avf_set_fused_variant(variant)
             for _ in range(3):
                 m.sformer(fm)
             e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
@@ -75,4 +69,4 @@ if __name__ == "__main__":
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
-            print(f"sformer 8192 frames fused={en} variant={variant}: {ms*1e3:.1f} us  {8192*53838848/ms/1e9:.1f} TFLOP/s")
+            print(f"sformer 8192 frames fused={en}: {ms*1e3:.1f} us  {8192*53838848/ms/1e9:.1f} TFLOP/s")
