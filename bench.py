@@ -1,8 +1,14 @@
 #!/usr/bin/env python
 """bench.py — AVFormer hot-path throughput on B200 (clips/s), with roofline and CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode fwd|train] [--check]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`--mode train` makes the hot-path TRAINING step (BASELINE config 4 restricted to the transformer stack: forward with tape,
+AULoss, backward, gradient all-reduce overlapped with the backward at N > 1, fused Adam) the measured thing, with the same JSON
+schema, its own end-to-end number and its own CPU reference arm (`--impl reference --mode train`).  `--check` (any N, meant
+for N > 1 under torchrun) runs the data-parallel parity checks instead of timing: the gathered logits of N ranks against the
+one-GPU result on the concatenated batch, and the all-reduced gradient bucket against the one-GPU large-batch gradient.
 
 A *step* is one pass of the transformer hot path (SFormer -> TFormer -> AU_former x2 ->
 fusion head -> logits/decisions) over one synthetic batch of 512 clips x 16 frames PER GPU (weak scaling;
@@ -127,10 +133,40 @@ def cpu_hot_path_clips_per_s(sample_clips, repeats, T=N_FRAMES):
     return sample_clips / best, best, torch.get_num_threads()
 
 
+def cpu_train_step_clips_per_s(sample_clips, repeats, T=N_FRAMES):
+    """Oracle port of one training step of the hot path on the host CPU: forward, AULoss, autograd backward, Adam on every
+    hot-path parameter (train.py:206-236)."""
+    import torch
+    from oracle import avformer_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    p = O.make_state_dict(SEED, T, hot_path_only=True)
+    stage3, frame, audio = O.synth_hot_path_inputs(SEED, sample_clips, T)
+    labels = (torch.rand(sample_clips, 12, generator=torch.Generator().manual_seed(SEED)) < 0.3).float()
+    state = {}
+
+    def one_step(step):
+        loss, grads, _, _ = O.hot_path_grads(stage3, frame, audio, labels, p, T, batch_stats=True, sformer_loss_weight=1.0)
+        for k, g in grads.items():
+            m, v = state.get(k, (torch.zeros_like(g), torch.zeros_like(g)))
+            p[k], m, v = O.adam_update(p[k], g, m, v, step, lr=5e-4, weight_decay=5e-5)
+            state[k] = (m, v)
+        return loss
+
+    one_step(1)                                                                        # warm-up
+    best = float("inf")
+    for r in range(repeats):
+        t0 = time.perf_counter()
+        one_step(2 + r)
+        best = min(best, time.perf_counter() - t0)
+    return sample_clips / best, best, torch.get_num_threads()
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.mode == "train":
+        return run_reference_arm_train(args)
     import torch
     from oracle import avformer_oracle as O
     torch.set_num_threads(os.cpu_count())
@@ -169,6 +205,64 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def run_reference_arm_train(args):
+    import torch
+    T = N_FRAMES
+    v1, t1, cores = cpu_train_step_clips_per_s(4, 1)                                    # size the per-step sample: ~100 s for the whole run
+    per_clip = t1 / 4
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    sample = int(max(2, min(TRAIN_CLIPS_PER_GPU, budget / per_clip)))
+    from oracle import avformer_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    p = O.make_state_dict(SEED, T, hot_path_only=True)
+    stage3, frame, audio = O.synth_hot_path_inputs(SEED, sample, T)
+    labels = (torch.rand(sample, 12, generator=torch.Generator().manual_seed(SEED)) < 0.3).float()
+    state = {}
+
+    def one_step(step):
+        _, grads, _, _ = O.hot_path_grads(stage3, frame, audio, labels, p, T, batch_stats=True, sformer_loss_weight=1.0)
+        for k, g in grads.items():
+            m, v = state.get(k, (torch.zeros_like(g), torch.zeros_like(g)))
+            p[k], m, v = O.adam_update(p[k], g, m, v, step, lr=5e-4, weight_decay=5e-5)
+            state[k] = (m, v)
+
+    for i in range(args.warmup):
+        one_step(1 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one_step(1 + args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(sample_note=f"each step = {sample} clips of the workload on the host CPU"),
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} clips x {T} frames per step, {args.steps} steps: oracle forward + autograd backward + Adam, torch {torch.__version__} fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+TRAIN_METRIC = "AVFormer hot-path training step clips/sec (fwd + bwd + fused Adam, gradient all-reduce at N>1)"
+
+
+def train_config(sample_note=None):
+    cfg = {"workload": f"avformer_hot_path_train: {TRAIN_CLIPS_PER_GPU} clips/GPU x {N_FRAMES} frames (BASELINE config 4 restricted to the transformer "
+                       f"stack: SFormer + TFormer + AU_former x2 + fusion head, all their parameters trainable, BatchNorm1d batch statistics, AULoss, "
+                       f"Adam(lr 5e-4, wd 5e-5) as train.py:334; the conv backbones are outside the hot path)",
+           "clips_per_gpu": TRAIN_CLIPS_PER_GPU, "n_frames": N_FRAMES,
+           "parallelism": "clip-sharded data parallel; the gradient bucket is all-reduced segment by segment (fusion head, AU_formers, TFormer, SFormer) "
+                          "as each stack finishes its backward, NCCL next to the backward kernels of the stacks below",
+           "l2": "per-step working set (activations tape ~0.4 GB) is larger than the 126 MB L2; no explicit flush",
+           "flop_per_clip": 3 * hot_path_flops_per_clip(N_FRAMES)}
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
 def workload_config(sample_note=None):
     cfg = {"workload": f"avformer_hot_path_eval: {CLIPS_PER_GPU} clips/GPU x {N_FRAMES} frames "
                        f"(SFormer on {CLIPS_PER_GPU * N_FRAMES} stage-3 maps [256,7,7] + TFormer + AU_former x2 + fusion head -> 12-AU logits)",
@@ -194,15 +288,22 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # The gathers are tiny ([512, 21] fp32 per rank): one or two NCCL channels are plenty, and every channel is a CTA that sits
-        # on an SM while the collective waits for the slowest rank.
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     T, B = N_FRAMES, CLIPS_PER_GPU
 
     torch.manual_seed(SEED)                      # random-init weights of the reference architecture (no checkpoints offline)
     model = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU")
     model = model.to(dev).eval().set_precision("bf16")
+    if args.check:
+        ok = run_dp_check(model, A, dev, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
+    if args.mode == "train":
+        run_train(model, A, dev, rank, world, args)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     g = torch.Generator(device="cpu").manual_seed(SEED + rank)
     host = {
@@ -260,10 +361,14 @@ def run_ours(args):
         L.avf_set_sm_cap(0)
 
         pipe = A.dp.PipelinedLogitGather()       # N > 1: the gather of batch i runs under the kernels of batch i+1
+        gather_mode = os.environ.get("AVF_GATHER", "pipelined")      # developer A/B: pipelined | instream | none
 
         def gstep():
             _, out21, _ = graphed.replay()
-            pipe.submit(out21)
+            if gather_mode == "pipelined":
+                pipe.submit(out21)
+            elif gather_mode == "instream" and world > 1:
+                dist.all_gather_into_tensor(gathered, out21)
 
         for _ in range(3):
             gstep()
@@ -276,6 +381,7 @@ def run_ours(args):
             e1.record()
             barrier()
         ms_total = e0.elapsed_time(e1)
+        parity = timed_outputs_vs_oracle(model, graphed.out, host, T) if rank == 0 else None
 
         # ---- end to end from pinned host buffers ---------------------------------------------
         out_host = torch.empty((B, 21), dtype=torch.float32).pin_memory()
@@ -316,12 +422,10 @@ def run_ours(args):
         roof = A.functional.sformer_roofline_probe(devin["stage3"], vm.s_former, time_fn) \
             if hasattr(A.functional, "sformer_roofline_probe") else None
 
-    ms_train, train_launches = train_step_ms(model, A, dev, rank, world, args)
-
-    t = torch.tensor([ms_total, ms_e2e, ms_train], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_train = t.tolist()
+    ms_total, ms_e2e = t.tolist()
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     peaks = measured_peaks()
@@ -363,17 +467,15 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "parity_max_err": parity["logits_max_abs_err"], "decisions_match": parity["decisions_match"], "parity": parity,
             "tensor_frac_whole_step": value / world * hot_path_flops_per_clip(T) / 1e12 / peaks["bf16_tflops_sustained"],
             "breakdown_ms": {"sformer": ms_sformer, "tformer": ms_tformer, "whole_step": ms_step, "whole_step_eager_launches": ms_eager},
+            "flops_per_clip": {"algorithmic": hot_path_flops_per_clip(T), "executed": hot_path_flops_per_clip(T) - tformer_skipped_flops_per_clip(T),
+                               "note": "executed = algorithmic minus the last TFormer layer's out-projection and MLP on the T non-cls rows, which "
+                                       "models/vformer.py:290 never reads (tensor_frac_whole_step uses the algorithmic count)"},
             "launch_mode": "one CUDA-graph replay per step (captured from the library's own kernel launches; gpu_launches counts the kernels inside it)"
                            + (f"; SFormer kernel on {sm_split[0]} SMs next to the TFormer/head chain on {sm_split[1]} SMs (avf_set_sm_cap)" if sm_split else ""),
-            "train": {"metric": "AVFormer hot-path training step clips/sec (fwd + bwd + fused Adam, gradient all-reduce at N>1)",
-                      "value": world * TRAIN_CLIPS_PER_GPU / (ms_train * 1e-3), "unit": "clips/s", "ms_per_step": ms_train,
-                      "clips_per_gpu": TRAIN_CLIPS_PER_GPU, "n_frames": T, "dtype": "bf16 operands, fp32 master weights / gradients / Adam state",
-                      "gpu_launches_per_step": train_launches,
-                      "tensor_frac": 3 * TRAIN_CLIPS_PER_GPU * hot_path_flops_per_clip(T) / (ms_train * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
-                      "note": "BASELINE config 4 restricted to the hot path: all transformer parameters train, BatchNorm1d batch statistics, "
-                              "Adam(lr 5e-4, wd 5e-5) as train.py:334; conv backbones are outside the hot path"},
+            "train": {"see": "python bench.py --mode train (its own JSON line, reference arm and end-to-end number)"},
         }
         print(json.dumps(line))
     if world > 1:
@@ -383,22 +485,55 @@ def run_ours(args):
 TRAIN_CLIPS_PER_GPU = 64
 
 
-def train_step_ms(model, A, dev, rank, world, args):
-    """One training step of the hot path (BASELINE config 4, transformer stack only): forward with tape, AULoss, backward,
-    FusedAdam (one flat-bucket all-reduce over NCCL at N>1 + one update kernel).  Returns (ms per step, launches per step)."""
+def tformer_skipped_flops_per_clip(T):
+    """Last TFormer layer, T non-cls rows: out-projection 2*I*D + MLP 4*D*M per row (D = I = 512, M = 1024)."""
+    return T * (2 * 512 * 512 + 4 * 512 * 1024)
+
+
+def timed_outputs_vs_oracle(model, outs, host, T, n_clips=8):
+    """Certify what was timed: the first `n_clips` clips of the LAST timed step's outputs (the graph's static output tensors)
+    against the fp64 oracle on the same inputs and weights.  Tolerances are north_star's bf16 ones."""
+    import torch
+    from oracle import avformer_oracle as O
+    s_out, out21, dec = outs
+    p = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
+    ref = O.hot_path_forward(host["stage3"][: n_clips * T].double(), host["frame"][: n_clips * T].double(), host["audio"][:n_clips].double(), p, T)
+    logits = out21[:n_clips, :12].double().cpu()
+    err = (logits - ref["logits"]).abs().max().item()
+    sure = ref["logits"].abs() > 2e-2
+    dec_ok = bool((((dec[:n_clips].cpu() > 0) == (ref["logits"] > 0)) | ~sure).all())
+    s_err = (s_out[: n_clips * T].double().cpu() - ref["sformer_out"]).abs()
+    return {"clips_checked": n_clips, "logits_max_abs_err": err, "logits_tolerance": 2e-2, "decisions_match": dec_ok,
+            "sformer_max_abs_err": s_err.max().item(), "sformer_mean_abs_err": s_err.mean().item(),
+            "ok": bool(err < 2e-2 and dec_ok and s_err.max().item() < 0.2),
+            "against": "oracle.hot_path_forward in fp64 on the same weights and the first clips of the timed batch"}
+
+
+def _hot_params(model):
+    return [p for k, p in model.named_parameters() if ".resnet." not in k and "s_former.conv1" not in k and "s_former.bn1" not in k
+            and "s_former.layer" not in k]
+
+
+def run_train(model, A, dev, rank, world, args):
+    """The hot-path training step as the measured thing (BASELINE config 4 restricted to the transformer stack)."""
     import torch
     import torch.distributed as dist
+    from avformer_b200.optim import segments_of
     T, B = N_FRAMES, TRAIN_CLIPS_PER_GPU
     g = torch.Generator(device="cpu").manual_seed(SEED + 100 + rank)
-    stage3 = torch.clamp(torch.randn(B * T, 256, 7, 7, generator=g) * 1.7 + 0.6, min=0).bfloat16().to(dev).requires_grad_(True)
-    frame = (torch.randn(B * T, 512, generator=g).abs() * 1.2).to(dev).requires_grad_(True)
-    audio = torch.randn(B, 512, generator=g).abs().to(dev).requires_grad_(True)
-    labels = (torch.rand(B, 12, generator=g) < 0.3).float().to(dev)
+    host = {
+        "stage3": torch.clamp(torch.randn(B * T, 256, 7, 7, generator=g) * 1.7 + 0.6, min=0).bfloat16().pin_memory(),
+        "frame": (torch.randn(B * T, 512, generator=g).abs() * 1.2).pin_memory(),
+        "audio": torch.randn(B, 512, generator=g).abs().pin_memory(),
+        "labels": (torch.rand(B, 12, generator=g) < 0.3).float().pin_memory(),
+    }
+    stage3 = host["stage3"].to(dev).requires_grad_(True)
+    frame = host["frame"].to(dev).requires_grad_(True)
+    audio = host["audio"].to(dev).requires_grad_(True)
+    labels = host["labels"].to(dev)
     probe = torch.randn(B * T, 256, 7, 7, generator=g).bfloat16().to(dev) * 1e-3          # stands in for d(loss)/d(sformer_out) from conv stage 4
     model.train()
-    hot = [p for k, p in model.named_parameters() if ".resnet." not in k and "s_former.conv1" not in k and "s_former.bn1" not in k
-           and "s_former.layer" not in k]
-    opt = A.FusedAdam(hot, lr=5e-4, weight_decay=5e-5)
+    opt = A.FusedAdam(_hot_params(model), lr=5e-4, weight_decay=5e-5, segments=segments_of(model))
     L = A._lib.lib()
 
     def eager_step():
@@ -416,23 +551,158 @@ def train_step_ms(model, A, dev, rank, world, args):
     eager_step()
     launches = int(L.avf_launch_count() - n0)
     graphed = A.GraphedTrainStep(model, opt, stage3, frame, audio, labels, probe)
-    step = graphed.step
-    for _ in range(3):
-        step()
-    steps = max(3, min(args.steps, 20))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        graphed.step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(dev.index) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            graphed.step()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+
+    # end to end: inputs and labels from pinned host memory every step, the loss read back
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        loss = graphed.step(host["stage3"], host["frame"], host["audio"], host["labels"])
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_step()
+    barrier()
     e0.record()
-    for _ in range(steps):
-        step()
+    for _ in range(e2e_steps):
+        e2e_step()
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / e2e_steps
+    final_loss = float(loss_host.item())
     model.eval()
-    return e0.elapsed_time(e1) / steps, launches
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / args.steps
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    flops_step = 3 * B * hot_path_flops_per_clip(T)
+    achieved = flops_step / (ms_step * 1e-3) / 1e12
+    bucket_bytes = sum(b["g"].numel() * 4 for b in opt._buckets if b is not None)
+    cpu_baseline = None
+    if world == 1:
+        sample = 4
+        cpu_v, cpu_t, cores = cpu_train_step_clips_per_s(sample, repeats=2)
+        cpu_baseline = {"value": cpu_v, "unit": "clips/s", "cores": cores, "kind": "port",
+                        "sample": f"{sample} clips x {T} frames, best of 2: oracle forward + autograd backward + Adam (torch fp32 CPU) of the same step"}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    line = {
+        "metric": TRAIN_METRIC, "value": world * B / (ms_step * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": train_config(), "clocks": clocks.summary(),
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+                "note": "GraphedTrainStep.step() fed from pinned host buffers (stage-3 maps, frame / audio features, labels) + D2H of the loss every step"},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                     "kernel": f"the whole training step ({launches} launches, none above 15 % of the step at 64 clips per GPU): algorithmic forward + backward "
+                               "FLOPs (3 x forward) over the step time",
+                     "peak_source": f"{peaks['source']} (sustained: a kernel chain timed inside a long step)", "algorithmic_flop_per_launch": flops_step},
+        "cpu_baseline": cpu_baseline,
+        "grad_bucket_bytes": bucket_bytes, "grad_allreduce": "per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer)" if world > 1 else None,
+        "final_loss": final_loss,
+        "launch_mode": "zero_grad + forward + AULoss + backward (+ the segment all-reduces at N>1) as ONE CUDA-graph replay, then the fused Adam launch",
+    }
+    print(json.dumps(line))
+
+
+def run_dp_check(model, A, dev, rank, world):
+    """SURVEY.md section 8(e) on hardware.  (1) evaluation: every rank runs the hot path on its own shard, the [N*b, 21] logits are
+    all-gathered over NCCL; rank 0 also runs all N shards as ONE batch on its GPU and compares.  (2) training: every rank
+    computes the gradients of its shard (BatchNorm1d on running statistics, no dropout: caveats 1 and 3), the bucket is
+    all-reduced by FusedAdam's segment reducer and scaled by 1/N; rank 0 compares with the gradient of the mean loss over
+    the concatenated batch computed on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from avformer_b200.optim import segments_of
+    T, b = N_FRAMES, 48
+
+    def inputs(r):
+        g = torch.Generator(device="cpu").manual_seed(SEED + 7 + r)
+        s3 = torch.clamp(torch.randn(b * T, 256, 7, 7, generator=g) * 1.7 + 0.6, min=0).bfloat16()
+        fr = (torch.randn(b * T, 512, generator=g).abs() * 1.2).bfloat16()
+        au = torch.randn(b, 512, generator=g).abs()
+        lab = (torch.rand(b, 12, generator=g) < 0.3).float()
+        return s3, fr, au, lab
+
+    mine = [t.to(dev) for t in inputs(rank)]
+    model.eval().set_dropout(0.0)
+    with torch.no_grad():
+        _, out21, dec = model.hot_path(mine[0], mine[1], mine[2], want_decisions=True)
+    gathered = A.dp.gather_logits(out21, world * b)
+    res = {"check": "dp_parity", "n_gpus": world, "clips_per_rank": b}
+    if rank == 0:
+        allin = [torch.cat([inputs(r)[i] for r in range(world)]).to(dev) for i in range(4)]
+        with torch.no_grad():
+            _, one, _ = model.hot_path(allin[0], allin[1], allin[2], want_decisions=True)
+        d = (gathered - one).abs().max().item()
+        res["logits_max_abs_diff"] = d
+        res["logits_bit_identical"] = bool(torch.equal(gathered, one))
+    # gradients
+    params = _hot_params(model)
+    for q in params:
+        q.grad = None
+    opt = A.FusedAdam(params, lr=0.0, segments=segments_of(model))
+
+    def grads(s3, fr, au, lab, reduce):
+        opt.zero_grad()
+        s_out, o = model.hot_path_train(s3.clone().requires_grad_(True), fr.float().requires_grad_(True), au.clone().requires_grad_(True))
+        loss = model.get_au_loss(o, lab) + 1e-3 * s_out.float().mean()
+        loss.backward()
+        if reduce:
+            opt.finish_reductions()
+        return loss.detach()
+
+    grads(*mine, reduce=False)
+    opt.step()                                       # lr 0: builds the flat bucket, changes nothing
+    grads(*mine, reduce=True)                        # armed now: segments are all-reduced from the backward bridges
+    bucket = opt._buckets[0]
+    red = bucket.get("reducer")
+    launched = list(red.launch_order) if red is not None else []
+    avg = bucket["g"].clone() / world
+    if red is not None:
+        red.disarm()
+    if rank == 0:
+        opt.overlap = False
+        opt._reducer = None
+        grads(*allin, reduce=False)                  # the same loss over the concatenated batch on ONE GPU (equal shard sizes: mean of means)
+        big = bucket["g"]
+        worst = 0.0
+        for q, o in zip(bucket["params"], bucket["offs"]):
+            n = q.numel()
+            ref = big[o:o + n]
+            scale = ref.abs().max().item()
+            if scale > 0:
+                worst = max(worst, (avg[o:o + n] - ref).abs().max().item() / scale)
+        res["grad_max_rel_err"] = worst
+        res["grad_segments_reduced_in_order"] = launched
+        res["ok"] = bool(res["logits_max_abs_diff"] <= 1e-5 and worst < 2e-3)
+        print(json.dumps(res))
+    ok = torch.tensor([1 if (rank != 0 or res.get("ok")) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(ok.item())
 
 
 def main():
@@ -441,6 +711,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="fwd", choices=["fwd", "train"], help="what a step is: the evaluation hot path (default) or its training step")
+    ap.add_argument("--check", action="store_true", help="data-parallel parity checks instead of timing (run under torchrun with N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -16,6 +16,26 @@ import torch
 from . import functional as AF
 
 
+# Listeners told which parameters' gradient kernels have just been enqueued on the current stream (optim.FusedAdam starts the
+# all-reduce of a bucket segment as soon as the last of its parameters is reported).  Called at the END of each bridge's backward.
+_GRAD_LISTENERS: List = []
+
+
+def add_grad_listener(fn) -> None:
+    if fn not in _GRAD_LISTENERS:
+        _GRAD_LISTENERS.append(fn)
+
+
+def remove_grad_listener(fn) -> None:
+    if fn in _GRAD_LISTENERS:
+        _GRAD_LISTENERS.remove(fn)
+
+
+def _notify(params) -> None:
+    for fn in _GRAD_LISTENERS:
+        fn(params)
+
+
 def _f32_dense(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
@@ -58,6 +78,7 @@ class EncoderStackFn(torch.autograd.Function):
         dx = _f32_dense(dy).clone()
         dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop, into=[p.grad for p in ctx.params])
         ctx.tape = None
+        _notify(ctx.params)
         return (dx if needs[0] else None, None, None, None, *grads)
 
 
@@ -90,6 +111,7 @@ class SFormerFn(torch.autograd.Function):
             dpos.view(-1, C)[: H * W] = AF.colsum(dx.view(F_, H * W * C)).view(H * W, C)
         dfmap = AF.sformer_tokens_unpack(dx, ctx.fshape, ctx.fdtype) if needs[0] else None
         (dpos,) = _hand_over((ctx.pos_param,), (dpos,))
+        _notify(ctx.params + (ctx.pos_param,))
         return (dfmap, dpos, None, *grads)
 
 
@@ -117,6 +139,7 @@ class TFormerEmbedFn(torch.autograd.Function):
             dpos = s.view(pshape) if needs[2] else None
             dcls = s[:dim].clone().view(cshape) if needs[1] else None
         dcls, dpos = _hand_over(ctx.params, (dcls, dpos))
+        _notify(ctx.params)
         return dframes, dcls, dpos, None
 
 
@@ -157,6 +180,7 @@ class AUFrontFn(torch.autograd.Function):
         if demb is not None:
             demb = demb.view(emb_shape).to(emb_dtype)
         pg = _hand_over(ctx.params, [dg if needs[1] else None, db if needs[2] else None, dbc.view(pos_shape).clone() if needs[3] else None] + wb_grads)
+        _notify(ctx.params)
         return (demb, pg[0], pg[1], pg[2], None, None, *pg[3:])
 
 
@@ -179,6 +203,7 @@ class AddPosFn(torch.autograd.Function):
             d = _f32_dense(dy)
             dpos = AF.colsum(d.view(d.shape[0] // period, period * d.shape[1])).view(pshape)
         (dpos,) = _hand_over(ctx.params, (dpos,))
+        _notify(ctx.params)
         return (dy if needs[0] else None), dpos, None
 
 
@@ -201,4 +226,5 @@ class AULogitsFn(torch.autograd.Function):
         want_dw = any(needs[3:])
         dx, dw = AF.au_logits_bwd(d, tok, last.w, n_clips, want_dx=needs[0], want_dw=want_dw)
         pg = _hand_over(ctx.params, [(dw[i:i + 1] if needs[3 + i] else None) for i in range(12)])
+        _notify(ctx.params)
         return (dx, None, None, *pg)

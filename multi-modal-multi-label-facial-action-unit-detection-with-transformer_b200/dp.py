@@ -84,3 +84,57 @@ class PipelinedLogitGather:
             if self.work[i] is not None:
                 self.work[i].wait()
                 self.work[i] = None
+
+
+class SegmentReducer:
+    """Gradient all-reduce overlapped with the backward pass.  The flat gradient bucket is laid out in contiguous segments, one
+    per stack, in the order the stacks finish their backward (optim.FusedAdam).  ``ready(params)`` is called whenever the kernels
+    producing some parameters' gradients have been enqueued; when the last parameter of a segment is reported its slice is
+    all-reduced asynchronously (NCCL runs it on its own stream, ordered behind the stream that called), so the reduction of the
+    fusion head's gradients travels over NVLink while the TFormer and SFormer are still in their backward.  ``finish()`` reduces
+    whatever was never reported and joins everything into the calling stream.  Sums only: the 1 / world_size of the mean is
+    folded into the optimiser's update kernel."""
+
+    def __init__(self, flat_grad: torch.Tensor, bounds, counts, seg_of: Dict[int, int], group=None):
+        self.g, self.bounds, self.counts, self.seg_of, self.group = flat_grad, list(bounds), list(counts), seg_of, group
+        self.armed = False
+        self.pending, self.works, self.launched = [], [], []
+        self.launch_order = []                       # segment indices in the order their reductions were started (tests)
+
+    def arm(self) -> None:
+        self.pending = list(self.counts)
+        self.works = [None] * len(self.bounds)
+        self.launched = [False] * len(self.bounds)
+        self.launch_order = []
+        self.armed = True
+
+    def disarm(self) -> None:
+        self.armed = False
+
+    def _launch(self, si: int) -> None:
+        lo, hi = self.bounds[si]
+        self.works[si] = dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.launched[si] = True
+        self.launch_order.append(si)
+
+    def ready(self, params) -> None:
+        if not self.armed:
+            return
+        for prm in params:
+            si = self.seg_of.get(id(prm))
+            if si is None or self.launched[si]:
+                continue
+            self.pending[si] -= 1
+            if self.pending[si] == 0:
+                self._launch(si)
+
+    def finish(self) -> None:
+        if not self.armed:
+            return
+        for si in range(len(self.bounds)):
+            if not self.launched[si]:
+                self._launch(si)
+        for i, w in enumerate(self.works):
+            if w is not None:
+                w.wait()
+                self.works[i] = None

@@ -35,6 +35,18 @@ def default_precision() -> str:
     return _DEFAULT_PRECISION
 
 
+def _rank_salt() -> int:
+    """0 on rank 0 / without a process group; otherwise a 62-bit hash of the data-parallel rank (murmur-style finaliser)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    h = (dist.get_rank() * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    h ^= h >> 31
+    h = (h * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    h ^= h >> 29
+    return h & ((1 << 62) - 1)
+
+
 def needs_grad(module: nn.Module, *inputs: torch.Tensor) -> bool:
     """True when autograd has to see this call: grad mode on and an input or a parameter of ``module`` requires grad.
     Such calls take the tape-keeping path (autograd.py); everything else takes the inference kernels."""
@@ -160,6 +172,10 @@ class Transformer(nn.Module):
         seed = self.fixed_dropout_seed
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            # Data parallel: every rank seeds torch identically (runner.py / train.py call manual_seed(seed) everywhere), so the draw
+            # above is the same on all ranks.  Mix the rank in, or all shards of the global batch would share their dropout masks
+            # (DDP and the single-GPU reference draw them independently per sample).
+            seed ^= _rank_salt()
         return float(self.dropout), seed, self.dropout_salt
 
     # -- forward -------------------------------------------------------------------------------

@@ -19,6 +19,30 @@ from . import _lib
 from .encoder import Transformer
 
 
+def weights_signature(model) -> tuple:
+    """Changes whenever a parameter or buffer of ``model`` may have changed: the optimiser epoch (FusedAdam writes parameters
+    through raw pointers) plus every tensor's version counter and address (load_state_dict, in-place edits, .to()).  A captured
+    graph holds raw pointers to the PACKED (bf16 / stacked / BN-folded) copies of the weights, which the eager path re-packs —
+    and frees — on such a change: a graph replayed afterwards would read stale weights or recycled memory."""
+    from . import functional as AF
+    v = 0
+    for t in list(model.parameters()) + list(model.buffers()):
+        v = (v * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+    return (AF.WEIGHTS_EPOCH, v)
+
+
+def _packed_refs(model) -> list:
+    """Strong references to every packed weight copy the model's modules currently cache (kept by a graph for as long as it may
+    replay with them)."""
+    keep = []
+    for mod in model.modules():
+        for name in ("_packed", "_front", "_last"):
+            obj = getattr(mod, name, None)
+            if obj is not None and not isinstance(obj, torch.nn.Module):
+                keep.append(obj)
+    return keep
+
+
 def _side_warmup(fn, iters: int = 3) -> None:
     """Warm-up on a side stream (allocations, lazy kernel attributes, weight packing) as torch.cuda.graph requires."""
     s = torch.cuda.Stream()
@@ -51,11 +75,17 @@ class GraphedHotPath:
         self.stage3, self.frame = stage3.clone(), frame.clone()
         self.audio = audio.float().clone()
         self.side = torch.cuda.Stream()
+        self.recaptures = 0
+        self._capture()
+
+    def _capture(self) -> None:
         with torch.no_grad():
             _side_warmup(self._run)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = self._run()
+        self._keep = _packed_refs(self.model)          # the graph reads these through raw pointers
+        self._sig = weights_signature(self.model)
 
     def _run(self):
         m = self.model
@@ -98,6 +128,11 @@ class GraphedHotPath:
             self.frame.copy_(frame, non_blocking=True)
         if audio is not None and audio.data_ptr() != self.audio.data_ptr():
             self.audio.copy_(audio, non_blocking=True)
+        if weights_signature(self.model) != self._sig:   # optimizer.step(), load_state_dict(), in-place edits: re-pack and capture again
+            if self.model.training:
+                raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
+            self.recaptures += 1
+            self._capture()
         self.graph.replay()
         return self.out
 
@@ -141,6 +176,8 @@ class GraphedTrainStep:
             torch.autograd.backward([loss, s_out], [None, self.d_s])
         else:
             loss.backward()
+        if hasattr(self.opt, "finish_reductions"):
+            self.opt.finish_reductions()                # data parallel: the segment all-reduces started during backward join here (inside the capture)
         return loss.detach()
 
     def step(self, stage3=None, frame=None, audio=None, labels=None):

@@ -75,11 +75,20 @@ class InferenceEngine:
         self.model = model
         self.dtype = backbone_dtype
         self.use_graphs = use_graphs
+        self.refolds = 0
+        self._fold()
+
+    def _fold(self) -> None:
+        """(Re-)fold the BatchNorm statistics into channels_last copies of the conv weights and drop every captured graph: the
+        copies, and the packed transformer weights the graphs point at, belong to ONE state of the model's parameters."""
+        from .graphs import weights_signature
+        model = self.model
         vm = model.video_model.video_model
-        self.video = _FoldedResNet(vm.s_former, backbone_dtype)
-        self.audio = _FoldedResNet(model.audio_model.audio_model.resnet, backbone_dtype)
+        self.video = _FoldedResNet(vm.s_former, self.dtype)
+        self.audio = _FoldedResNet(model.audio_model.audio_model.resnet, self.dtype)
         self.num_channels = vm.num_channels
         self._graphs: Dict[tuple, tuple] = {}
+        self._sig = weights_signature(model)
 
     # -- eager forward (also what gets captured) ---------------------------------------------------------------
     @torch.no_grad()
@@ -109,6 +118,12 @@ class InferenceEngine:
         clip, audio = x["clip"], x["audio_features"]
         AF._cuda(clip, "x['clip']")
         AF._cuda(audio, "x['audio_features']")
+        from .graphs import weights_signature, _packed_refs
+        if weights_signature(self.model) != self._sig:        # load_state_dict / optimizer.step() / in-place edits since the fold
+            if self.model.training:
+                raise RuntimeError("InferenceEngine folds the eval-mode BatchNorm statistics: call model.eval() first")
+            self.refolds += 1
+            self._fold()
         if not self.use_graphs:
             return self._forward(clip, audio)
         key = (tuple(clip.shape), clip.dtype, tuple(audio.shape), audio.dtype)
@@ -125,8 +140,8 @@ class InferenceEngine:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._forward(s_clip, s_audio)
-            ent = self._graphs[key] = (g, s_clip, s_audio, out)
-        g, s_clip, s_audio, out = ent
+            ent = self._graphs[key] = (g, s_clip, s_audio, out, _packed_refs(self.model))   # the graph reads the packed weights through raw pointers
+        g, s_clip, s_audio, out, _ = ent
         s_clip.copy_(clip, non_blocking=True)
         s_audio.copy_(audio, non_blocking=True)
         g.replay()

@@ -9,29 +9,61 @@ gradient over the data-parallel group (NCCL over NVLink; skipped for a single pr
 (``avf_adam_step``) that folds the 1/world_size of the gradient mean into the update.  Parameters that never receive a
 gradient (frozen sub-models, the per-modality ``AU_linear_last*`` whose result the AVFormer discards) are left
 untouched, exactly like torch.optim.Adam skips ``grad is None``.
+
+Overlap with the backward pass (train.py:235-236 is "backward, then step"; data parallel adds the reduction in between):
+``FusedAdam(..., segments=[[params of stack A], [params of stack B], ...])`` lays the bucket out segment by segment, in the
+order the stacks FINISH their backward (fusion head first, SFormer last: ``segments_of(model)``).  The autograd bridges
+report finished parameter gradients (``autograd.add_grad_listener``); as soon as a segment is complete its slice of the bucket
+is all-reduced asynchronously, NCCL running it on its own stream next to the backward kernels of the stacks below, and
+``step()`` applies the update segment by segment as the reductions land.  ``finish_reductions()`` joins the outstanding
+ones (a CUDA-graph capture of forward + backward calls it before the capture ends, so the collectives are part of the graph).
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+import os
+import weakref
+from typing import Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
 
 from . import functional as AF
+from .dp import SegmentReducer
 
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 decoupled: bool = False, process_group=None):
+                 decoupled: bool = False, process_group=None, segments: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None,
+                 overlap: Optional[bool] = None):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("FusedAdam: invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled))
         self.process_group = process_group
         self._buckets: List[Optional[dict]] = [None] * len(self.param_groups)
+        # reduction segments (single parameter group only): parameter id -> segment index, in backward-completion order
+        self._seg_of = {}
+        if segments is not None:
+            if len(self.param_groups) != 1:
+                raise ValueError("FusedAdam: reduction segments need a single parameter group")
+            for si, seg in enumerate(segments):
+                for prm in seg:
+                    self._seg_of[id(prm)] = si
+        self._n_seg = (max(self._seg_of.values()) + 1) if self._seg_of else 1
+        self.overlap = (os.environ.get("AVF_OVERLAP_REDUCE", "1") != "0") if overlap is None else bool(overlap)
+        self._reducer: Optional[SegmentReducer] = None
+        self._listening = False
+        weakself = weakref.ref(self)
+
+        def _on_ready(ps):
+            me = weakself()
+            if me is not None:
+                me._grads_ready(ps)
+        self._listener = _on_ready
 
     # -- bucket construction -------------------------------------------------------------------
-    @staticmethod
-    def _flatten(params: List[torch.nn.Parameter]) -> dict:
+    def _flatten(self, params: List[torch.nn.Parameter]) -> dict:
+        # segment by segment (stable inside a segment); parameters outside every segment form the last one
+        params = sorted(params, key=lambda q: self._seg_of.get(id(q), self._n_seg))
         dev = params[0].device
         offs, n = [], 0
         for p in params:
@@ -48,10 +80,60 @@ class FusedAdam(torch.optim.Optimizer):
                 p.data = flat_p[o:o + p.numel()].view(p.shape)
                 p.grad = flat_g[o:o + p.numel()].view(p.shape)
         shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)       # bf16 copy of the bucket, refreshed by the update kernel
-        return dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0)
+        bounds, counts = [], []                                          # [lo, hi) of each non-empty segment in the bucket
+        for si in range(self._n_seg + 1):
+            idx = [i for i, q in enumerate(params) if self._seg_of.get(id(q), self._n_seg) == si]
+            if idx:
+                lo = offs[idx[0]]
+                hi = offs[idx[-1] + 1] if idx[-1] + 1 < len(params) else n
+                bounds.append((lo, hi))
+                counts.append(len(idx))
+        seg_of = {}
+        for si, (lo, hi) in enumerate(bounds):                          # re-index to the non-empty segments, bucket members only
+            for q, o in zip(params, offs):
+                if lo <= o < hi:
+                    seg_of[id(q)] = si
+        self._seg_of = seg_of
+        self._n_seg = len(bounds)
+        return dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
+                    bounds=bounds, counts=counts)
+
+    # -- overlapped gradient reduction (dp.SegmentReducer does the bookkeeping) ----------------------
+    def _world(self) -> int:
+        return dist.get_world_size(self.process_group) if dist.is_initialized() else 1
+
+    def _arm(self) -> None:
+        """Start of a backward pass: every segment waits for all of its parameters again."""
+        b = self._buckets[0] if len(self._buckets) == 1 else None
+        if b is None or not self.overlap or self._world() == 1:
+            self._reducer = None
+            return
+        if b.get("reducer") is None:
+            b["reducer"] = SegmentReducer(b["g"], b["bounds"], b["counts"], self._seg_of, self.process_group)
+        self._reducer = b["reducer"]
+        self._reducer.arm()
+        if not self._listening:
+            from . import autograd as AG
+            AG.add_grad_listener(self._listener)
+            self._listening = True
+
+    def _grads_ready(self, params) -> None:
+        """Called by the autograd bridges once the kernels that accumulate these parameters' gradients are enqueued."""
+        if self._reducer is not None:
+            self._reducer.ready(params)
+
+    def finish_reductions(self) -> None:
+        """Join every outstanding segment reduction into the current stream (segments whose completion was never reported —
+        a stack whose inputs need no gradient reports nothing — are reduced here)."""
+        if self._reducer is not None:
+            self._reducer.finish()
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         """Bucketed parameters keep their flat gradient views (zeroed with one memset); others follow torch's semantics."""
+        self._zero_grad(set_to_none)
+        self._arm()
+
+    def _zero_grad(self, set_to_none: bool = True) -> None:
         for gi, group in enumerate(self.param_groups):
             b = self._buckets[gi]
             bucketed = set()
@@ -76,13 +158,13 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        world = dist.get_world_size(self.process_group) if dist.is_initialized() else 1
+        world = self._world()
         for gi, group in enumerate(self.param_groups):
             with_grad = [p for p in group["params"] if p.grad is not None]
             if not with_grad:
                 continue
             b = self._buckets[gi]
-            if b is None or [id(p) for p in b["params"]] != [id(p) for p in with_grad]:
+            if b is None or {id(p) for p in b["params"]} != {id(p) for p in with_grad}:
                 if b is not None:
                     raise RuntimeError("FusedAdam: the set of parameters receiving gradients changed after the first step")
                 b = self._buckets[gi] = self._flatten(with_grad)
@@ -92,7 +174,10 @@ class FusedAdam(torch.optim.Optimizer):
                     if p.grad.data_ptr() != view.data_ptr():
                         view.copy_(p.grad)
                         p.grad = view
-            if world > 1:
+            if world > 1 and self._reducer is not None and self._reducer.armed:
+                self._reducer.finish()                            # segments were armed for this backward pass: reduce / join what is left
+                self._reducer.disarm()
+            elif world > 1:
                 dist.all_reduce(b["g"], op=dist.ReduceOp.SUM, group=self.process_group)
             b["step"] += 1
             AF.adam_step_(b["p"], b["g"], b["m"], b["v"], b["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
@@ -104,3 +189,14 @@ class FusedAdam(torch.optim.Optimizer):
                     p._avf_bf16 = (b["shadow"][o:o + p.numel()].view(p.shape), p._version)
         AF.bump_weights_epoch()
         return loss
+
+
+def segments_of(model) -> List[List[torch.nn.Parameter]]:
+    """The AVFormer's trainable hot-path parameters grouped by stack, in the order the stacks finish their backward pass
+    (models/avformer.py:93-106 read backwards): fusion head, video AU_former, audio AU_former, TFormer, SFormer.  Everything else
+    (conv backbones) forms a last segment."""
+    groups = [model.au_head, model.video_model.au_head, model.audio_model.au_head, model.video_model.video_model.t_former]
+    segs = [[q for q in g.parameters() if q.requires_grad] for g in groups]
+    sf = model.video_model.video_model.s_former
+    segs.append([q for n, q in sf.named_parameters() if q.requires_grad and (n.startswith("spatial_transformer.") or n == "pos_embedding")])
+    return segs

@@ -58,6 +58,37 @@ def _worker(rank, world, port, out_dir):
         for step, got in outs[1:]:                                      # (outs[0] shares its buffers with step 2)
             for r in range(world):
                 assert torch.equal(got[4 * r: 4 * r + 4], torch.full((4, 21), float(10 * step + r)))
+        # segment-wise gradient reduction overlapped with backward (optim.FusedAdam at N > 1): three segments of a flat bucket,
+        # parameters reported stack by stack in backward order; the last segment is never reported and is reduced by finish()
+        prm = [torch.nn.Parameter(torch.zeros(n)) for n in (3, 5, 2, 4, 6)]
+        seg_of = {id(prm[0]): 0, id(prm[1]): 0, id(prm[2]): 1, id(prm[3]): 1, id(prm[4]): 2}
+        flat = torch.arange(24, dtype=torch.float32) * (rank + 1)                   # offsets 0,3 | 8,10 | 16 (8-aligned like FusedAdam)
+        red = A.dp.SegmentReducer(flat, bounds=[(0, 8), (8, 16), (16, 24)], counts=[2, 2, 1], seg_of=seg_of)
+        red.arm()
+        red.ready([prm[3]])
+        assert red.launch_order == []                                               # segment 1 still waits for prm[2]
+        red.ready([prm[0], prm[1]])
+        assert red.launch_order == [0]
+        red.ready([prm[2]])
+        assert red.launch_order == [0, 1]
+        red.ready([prm[2]])                                                         # a second report of a launched segment is ignored
+        red.finish()
+        assert red.launch_order == [0, 1, 2]
+        assert torch.equal(flat, torch.arange(24, dtype=torch.float32) * 3.0)       # (1 + 2) x: every element summed exactly once
+        red.disarm()
+        red.ready([prm[4]])                                                         # not armed: nothing happens
+        assert torch.equal(flat, torch.arange(24, dtype=torch.float32) * 3.0)
+        # dropout seeds: identical torch seeds on every rank must still give rank-dependent mask seeds (encoder._rank_salt)
+        from avformer_b200.encoder import _rank_salt
+        salts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(salts, torch.tensor([_rank_salt()], dtype=torch.int64))
+        assert int(salts[0]) == 0 and len({int(v) for v in salts}) == world
+        tr = A.Transformer(128, 1, 8, 32, 256, dropout=0.2).train()
+        torch.manual_seed(1234)
+        _, seed, _ = tr.dropout_state()
+        seeds = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(seeds, torch.tensor([seed], dtype=torch.int64))
+        assert len({int(v) for v in seeds}) == world
         np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     finally:
         dist.destroy_process_group()

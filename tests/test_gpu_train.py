@@ -410,6 +410,55 @@ def test_graphed_hot_path_equals_eager(sm_split):
             assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
 
 
+def test_graphed_hot_path_notices_weight_changes():
+    """A captured graph points at the packed (bf16 / stacked) copies of the weights.  After optimizer.step(), load_state_dict() or an
+    in-place edit the eager path re-packs and frees them; the graph has to notice and capture again instead of replaying with stale
+    weights or recycled memory."""
+    T, B, seed = 16, 4, 63
+    m = _model(seed, T, "bf16", dropout=0.0)
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    dev = (stage3.bfloat16().cuda(), frame.bfloat16().cuda(), audio.cuda())
+    labels = O.synth_inputs(seed, B, T, image=8)[2].cuda()
+    m.eval()
+    with torch.no_grad():
+        g = A.GraphedHotPath(m, *dev)
+        first = [t.clone() for t in g.replay(*dev)]
+        assert g.recaptures == 0
+
+    def check(expect_new_capture):
+        m.eval()
+        with torch.no_grad():
+            ref = [t.clone() for t in m.hot_path(*dev, want_decisions=True)]
+            n0 = g.recaptures
+            got = g.replay(*dev)
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(ref, got))
+            assert (g.recaptures > n0) == expect_new_capture
+        return ref
+
+    check(False)
+    # (1) one training step of the fusion head through FusedAdam (raw-pointer update + bf16 shadow)
+    m.train()
+    opt = A.FusedAdam(list(m.au_head.parameters()) + list(m.video_model.video_model.s_former.spatial_transformer.parameters()), lr=1e-2)
+    for _ in range(2):
+        opt.zero_grad()
+        s_out, out21 = m.hot_path_train(dev[0].clone().requires_grad_(True), dev[1].float().requires_grad_(True), dev[2].clone().requires_grad_(True))
+        (m.get_au_loss(out21, labels) + s_out.float().mean()).backward()
+        opt.step()
+    after_step = check(True)
+    assert not torch.equal(after_step[1], first[1]) and not torch.equal(after_step[0], first[0])
+    check(False)
+    # (2) load_state_dict of different weights
+    m.load_state_dict(O.make_state_dict(seed + 1, T), strict=True)
+    after_load = check(True)
+    assert not torch.equal(after_load[1], after_step[1])
+    # (3) an in-place edit of one parameter
+    with torch.no_grad():
+        m.video_model.video_model.t_former.cls_token.mul_(1.5)
+    check(True)
+    check(False)
+
+
 def test_programmatic_dependent_launch_does_not_change_results():
     """Every kernel is launched with the programmatic-stream-serialization attribute and waits (griddepcontrol.wait) for its
     predecessor before touching memory: results must be bit-identical to plain launches (avf_set_pdl_enabled(0))."""
