@@ -254,8 +254,8 @@ def train_config(sample_note=None):
                        f"stack: SFormer + TFormer + AU_former x2 + fusion head, all their parameters trainable, BatchNorm1d batch statistics, AULoss, "
                        f"Adam(lr 5e-4, wd 5e-5) as train.py:334; the conv backbones are outside the hot path)",
            "clips_per_gpu": TRAIN_CLIPS_PER_GPU, "n_frames": N_FRAMES,
-           "parallelism": "clip-sharded data parallel; the gradient bucket is all-reduced segment by segment (fusion head, AU_formers, TFormer, SFormer) "
-                          "as each stack finishes its backward, NCCL next to the backward kernels of the stacks below",
+           "parallelism": "clip-sharded data parallel; one NCCL sum-all-reduce of the flat fp32 gradient bucket behind the backward pass, 1/N folded into "
+                          "the fused Adam kernel (AVF_OVERLAP_REDUCE=1: per-stack segments reduced from the backward bridges instead, measured slower)",
            "l2": "per-step working set (activations tape ~0.4 GB) is larger than the 126 MB L2; no explicit flush",
            "flop_per_clip": 3 * hot_path_flops_per_clip(N_FRAMES)}
     if sample_note:
@@ -266,7 +266,7 @@ def train_config(sample_note=None):
 def workload_config(sample_note=None):
     cfg = {"workload": f"avformer_hot_path_eval: {CLIPS_PER_GPU} clips/GPU x {N_FRAMES} frames "
                        f"(SFormer on {CLIPS_PER_GPU * N_FRAMES} stage-3 maps [256,7,7] + TFormer + AU_former x2 + fusion head -> 12-AU logits)",
-           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel, logit all-gather at N>1 (asynchronous: the gather of batch i overlaps the kernels of batch i+1, all gathers complete inside the timed region)",
+           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel; at N>1 every step ends with the NCCL all-gather of the [512, 21] logits of all ranks, in the stream, inside the timed region",
            "l2": "inputs (205 MB of stage-3 maps per step) are larger than the 126 MB L2; no explicit flush",
            "flop_per_clip": hot_path_flops_per_clip(N_FRAMES)}
     if sample_note:
@@ -350,18 +350,19 @@ def run_ours(args):
         sm_split = None
         if os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
             sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
-        # N > 1: the asynchronous gather of batch i runs while batch i+1 computes.  A persistent kernel with one CTA per SM would find
-        # the SMs of the NCCL CTAs taken, and the displaced CTAs (static tile striding) would finish late: leave those SMs out of the
-        # persistent grids (4096 SFormer tiles are 28 per CTA on 146 CTAs as on 148).
+        # AVF_SM_RESERVE=k (developer A/B, goes with AVF_GATHER=pipelined): leave k SMs out of the persistent grids for the NCCL CTAs of
+        # an asynchronous gather — measured slower on 2 and 8 GPUs than the plain in-stream gather on all SMs, so 0 by default.
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_reserve = int(os.environ.get("AVF_SM_RESERVE", "2" if world > 1 else "0"))
+        sm_reserve = int(os.environ.get("AVF_SM_RESERVE", "0"))
         if sm_reserve > 0:
             L.avf_set_sm_cap(n_sm - sm_reserve)
         graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split)
         L.avf_set_sm_cap(0)
 
         pipe = A.dp.PipelinedLogitGather()       # N > 1: the gather of batch i runs under the kernels of batch i+1
-        gather_mode = os.environ.get("AVF_GATHER", "pipelined")      # developer A/B: pipelined | instream | none
+        # in the stream, right behind the step's last kernel: measured on 8 B200s 1.309 ms per step against 1.317 ms for the asynchronous
+        # pipelined gather with two SMs reserved for NCCL (AVF_GATHER=pipelined AVF_SM_RESERVE=2) and 1.255 ms without any gather
+        gather_mode = os.environ.get("AVF_GATHER", "instream")      # developer A/B: instream | pipelined | none
 
         def gstep():
             _, out21, _ = graphed.replay()
@@ -620,7 +621,7 @@ def run_train(model, A, dev, rank, world, args):
                                "FLOPs (3 x forward) over the step time",
                      "peak_source": f"{peaks['source']} (sustained: a kernel chain timed inside a long step)", "algorithmic_flop_per_launch": flops_step},
         "cpu_baseline": cpu_baseline,
-        "grad_bucket_bytes": bucket_bytes, "grad_allreduce": "per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer)" if world > 1 else None,
+        "grad_bucket_bytes": bucket_bytes, "grad_allreduce": ("per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer)" if opt.overlap else "one all-reduce of the flat bucket after backward") if world > 1 else None,
         "final_loss": final_loss,
         "launch_mode": "zero_grad + forward + AULoss + backward (+ the segment all-reduces at N>1) as ONE CUDA-graph replay, then the fused Adam launch",
     }
@@ -663,7 +664,7 @@ def run_dp_check(model, A, dev, rank, world):
     params = _hot_params(model)
     for q in params:
         q.grad = None
-    opt = A.FusedAdam(params, lr=0.0, segments=segments_of(model))
+    opt = A.FusedAdam(params, lr=0.0, segments=segments_of(model), overlap=True)
 
     def grads(s3, fr, au, lab, reduce):
         opt.zero_grad()

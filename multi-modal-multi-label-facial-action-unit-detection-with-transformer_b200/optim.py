@@ -49,7 +49,11 @@ class FusedAdam(torch.optim.Optimizer):
                 for prm in seg:
                     self._seg_of[id(prm)] = si
         self._n_seg = (max(self._seg_of.values()) + 1) if self._seg_of else 1
-        self.overlap = (os.environ.get("AVF_OVERLAP_REDUCE", "1") != "0") if overlap is None else bool(overlap)
+        # Off by default: measured on 2 and 8 B200s (bench.py --mode train, 64 clips per GPU) the overlapped reduction is SLOWER than one
+        # all-reduce behind the backward (2.42 vs 2.28 ms, 2.59 vs 2.46 ms; one GPU 2.17 ms) — the NCCL CTAs take SMs away from the
+        # persistent, statically striding backward GEMMs, whose displaced CTAs finish their tile share late.  AVF_OVERLAP_REDUCE=1 or
+        # overlap=True turns it on (the data-parallel parity check, bench.py --check, always exercises it).
+        self.overlap = (os.environ.get("AVF_OVERLAP_REDUCE", "0") == "1") if overlap is None else bool(overlap)
         self._reducer: Optional[SegmentReducer] = None
         self._listening = False
         weakself = weakref.ref(self)
