@@ -945,9 +945,13 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
 
 template <int IO, int NTOK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __grid_constant__ FusedArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (threadIdx.x == 0 && (smem - smem_raw) + SMEM_USED > SMEM_ALLOC) {
+  // The kernel has no static shared memory, so the dynamic window starts at the CTA's shared-memory base, which is 1024-byte
+  // aligned (checked below).  Using the array itself — not an address rounded up through integer arithmetic — lets the compiler
+  // see that every access is to the shared state space: 32-bit LDS / STS with immediate offsets instead of generic LD / ST with
+  // 64-bit address arithmetic (IADD3 + IMAD.X per access in the worker sweeps).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0u) {
     printf("avf: encoder_fused_kernel: dynamic shared memory base is not 1024-byte aligned enough\n");
     __trap();
   }
