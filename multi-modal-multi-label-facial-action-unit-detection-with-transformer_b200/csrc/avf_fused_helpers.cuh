@@ -97,6 +97,59 @@ __device__ __forceinline__ uint32_t gelu_bf16x2(uint32_t x) {
   const uint32_t hx = mul_bf16x2(x, HALF);
   return fma_bf16x2(hx, tanh_bf16x2(u), hx);
 }
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: one instruction, two fp32 results, bit-identical to the scalar forms).  The
+// row workers are bound by the issue rate of their fp32 sweeps (LayerNorm statistics / normalisation, bias and positional adds,
+// softmax scaling), so halving the instruction count of those loops is worth more than any reordering.  A pair lives in a 64-bit
+// register; consecutive TMEM columns land in consecutive registers, so building a pair from two of them costs nothing.
+// -DAVF_F32X2=0 restores the scalar forms.
+#ifndef AVF_F32X2
+#define AVF_F32X2 1
+#endif
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+#if AVF_F32X2
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+#else
+  float al, ah, bl, bh;
+  f2_unpack(a, al, ah); f2_unpack(b, bl, bh);
+  return f2_pack(al + bl, ah + bh);
+#endif
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+#if AVF_F32X2
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+#else
+  float al, ah, bl, bh;
+  f2_unpack(a, al, ah); f2_unpack(b, bl, bh);
+  return f2_pack(al * bl, ah * bh);
+#endif
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+#if AVF_F32X2
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+#else
+  float al, ah, bl, bh, cl, ch;
+  f2_unpack(a, al, ah); f2_unpack(b, bl, bh); f2_unpack(c, cl, ch);
+  return f2_pack(fmaf(al, bl, cl), fmaf(ah, bh, ch));
+#endif
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2_pair(uint64_t v) {      // (lo, hi) fp32 pair -> packed bf16 pair, round to nearest even
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return cvt_bf16x2(lo, hi);
+}
+
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"

@@ -188,12 +188,20 @@ struct Worker {
     float shift, s, ss;
     __device__ __forceinline__ void add(const float (&x)[32], bool first) {
       if (first) shift = x[0];
+      // pairs: d = x - shift, s += d, ss += d * d as three packed instructions per two elements
+      const uint64_t nshift = f2_pack(-shift, -shift);
+      uint64_t s2 = f2_pack(0.f, 0.f), q2 = s2;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = x[j] - shift;
-        s += d;
-        ss = fmaf(d, d, ss);
+      for (int j = 0; j < 32; j += 2) {
+        const uint64_t d = f2_add(f2_pack(x[j], x[j + 1]), nshift);
+        s2 = f2_add(s2, d);
+        q2 = f2_fma(d, d, q2);
       }
+      float a, b;
+      f2_unpack(s2, a, b);
+      s += a + b;
+      f2_unpack(q2, a, b);
+      ss += a + b;
     }
   };
   __device__ __forceinline__ void finish_stats(const Stats& st, float& mean, float& rstd) {
@@ -222,6 +230,7 @@ struct Worker {
   __device__ __forceinline__ void normalize_from_tmem(float mean, float rstd, int ln_sel, int v_next_bias) {
     const int cbase = g * CW;
     const float nmr = -mean * rstd;
+    const uint64_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
 #pragma unroll 1
     for (int c0 = 0; c0 < CW; c0 += 32) {
       float x[32];
@@ -235,16 +244,17 @@ struct Worker {
         const __nv_bfloat16* v16 = reinterpret_cast<const __nv_bfloat16*>(vec + V_B16) + ln_sel * 512 + col0 + ch * 8;
         const uint4 gm = *reinterpret_cast<const uint4*>(v16), bt = *reinterpret_cast<const uint4*>(v16 + 256);
         uint4 pk;
-        pk.x = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8], rstd, nmr), fmaf(x[ch * 8 + 1], rstd, nmr)), gm.x, bt.x);
-        pk.y = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 2], rstd, nmr), fmaf(x[ch * 8 + 3], rstd, nmr)), gm.y, bt.y);
-        pk.z = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 4], rstd, nmr), fmaf(x[ch * 8 + 5], rstd, nmr)), gm.z, bt.z);
-        pk.w = fma_bf16x2(cvt_bf16x2(fmaf(x[ch * 8 + 6], rstd, nmr), fmaf(x[ch * 8 + 7], rstd, nmr)), gm.w, bt.w);
+        pk.x = fma_bf16x2(cvt_bf16x2_pair(f2_fma(f2_pack(x[ch * 8], x[ch * 8 + 1]), rstd2, nmr2)), gm.x, bt.x);
+        pk.y = fma_bf16x2(cvt_bf16x2_pair(f2_fma(f2_pack(x[ch * 8 + 2], x[ch * 8 + 3]), rstd2, nmr2)), gm.y, bt.y);
+        pk.z = fma_bf16x2(cvt_bf16x2_pair(f2_fma(f2_pack(x[ch * 8 + 4], x[ch * 8 + 5]), rstd2, nmr2)), gm.z, bt.z);
+        pk.w = fma_bf16x2(cvt_bf16x2_pair(f2_fma(f2_pack(x[ch * 8 + 6], x[ch * 8 + 7]), rstd2, nmr2)), gm.w, bt.w);
         *reinterpret_cast<uint4*>(dst + (((chunk0 + ch) ^ (row & 7)) << 4)) = pk;
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(vec + v_next_bias + col0 + j);
-        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(vec + v_next_bias + col0 + j);      // two fp32 pairs
+        f2_unpack(f2_add(f2_pack(x[j], x[j + 1]), b.x), x[j], x[j + 1]);
+        f2_unpack(f2_add(f2_pack(x[j + 2], x[j + 3]), b.y), x[j + 2], x[j + 3]);
       }
       tmem_st32(tl + TM_X + col0, reinterpret_cast<const uint32_t(&)[32]>(x));
     }
@@ -282,7 +292,9 @@ __device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t 
   const float mrow = w.exchange_max(mloc);      // also orders every S load of the row before any P store (P overwrites S)
   pf.mark(PW_E2_XCH);
   const float nml = -mrow * sm_scale;
-  float sum_lo = 0.f, sum_hi = 0.f;              // low / high halves of the pairs: two independent chains
+  const uint64_t sc2 = f2_pack(sm_scale, sm_scale), nml2 = f2_pack(nml, nml);
+  uint64_t sum2 = f2_pack(0.f, 0.f);             // (sum of the low halves, sum of the high halves) of the exponentiated pairs
+  float sum_lo = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int nv = (TAILV > 0 && c == NC - 1) ? TAILV : 8;
@@ -290,9 +302,8 @@ __device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (2 * j + 1 < nv) {
-        e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), fmaf(s[c][2 * j + 1], sm_scale, nml)));
-        sum_lo += __uint_as_float(e[j] << 16);
-        sum_hi += __uint_as_float(e[j] & 0xFFFF0000u);
+        e[j] = ex2_bf16x2(cvt_bf16x2_pair(f2_fma(f2_pack(s[c][2 * j], s[c][2 * j + 1]), sc2, nml2)));
+        sum2 = f2_add(sum2, f2_pack(__uint_as_float(e[j] << 16), __uint_as_float(e[j] & 0xFFFF0000u)));
       } else if (2 * j < nv) {                   // only the low half of the pair exists
         e[j] = ex2_bf16x2(cvt_bf16x2(fmaf(s[c][2 * j], sm_scale, nml), -INFINITY)) & 0xFFFFu;
         sum_lo += __uint_as_float(e[j] << 16);
@@ -302,7 +313,9 @@ __device__ __forceinline__ float softmax_fixed(Worker& w, uint32_t ts, uint32_t 
     }
     tmem_st4(tp + c * 4, e[0], e[1], e[2], e[3]);
   }
-  return sum_lo + sum_hi;
+  float a, b;
+  f2_unpack(sum2, a, b);
+  return sum_lo + (a + b);
 }
 
 __host__ __device__ constexpr int slot_of(int n_tok) { return n_tok <= 16 ? 16 : (n_tok <= 32 ? 32 : 64); }
@@ -378,10 +391,10 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
 #endif
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            x[4 * j] = __bfloat162float(src16[(c0 + 4 * j) * n_tok]) + p[j].x;
-            x[4 * j + 1] = __bfloat162float(src16[(c0 + 4 * j + 1) * n_tok]) + p[j].y;
-            x[4 * j + 2] = __bfloat162float(src16[(c0 + 4 * j + 2) * n_tok]) + p[j].z;
-            x[4 * j + 3] = __bfloat162float(src16[(c0 + 4 * j + 3) * n_tok]) + p[j].w;
+            f2_unpack(f2_add(f2_pack(__bfloat162float(src16[(c0 + 4 * j) * n_tok]), __bfloat162float(src16[(c0 + 4 * j + 1) * n_tok])),
+                             f2_pack(p[j].x, p[j].y)), x[4 * j], x[4 * j + 1]);
+            f2_unpack(f2_add(f2_pack(__bfloat162float(src16[(c0 + 4 * j + 2) * n_tok]), __bfloat162float(src16[(c0 + 4 * j + 3) * n_tok])),
+                             f2_pack(p[j].z, p[j].w)), x[4 * j + 2], x[4 * j + 3]);
           }
         } else {
           float4 p4[8];
@@ -483,11 +496,15 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           uint8_t* ob = smem + OFF_OST + row * 64;
           const uint32_t sw = uint32_t((row >> 1) & 3);
 #pragma unroll
-          for (int c = 0; c < OW / 8; ++c) {
-            float y[8];
+          const uint64_t inv2 = f2_pack(inv_l, inv_l);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(r[c * 8 + j]) * inv_l;
-            *reinterpret_cast<uint4*>(ob + ((uint32_t(g * (OW / 8) + c) ^ sw) << 4)) = pack8(y);
+          for (int c = 0; c < OW / 8; ++c) {
+            uint4 pk;
+            pk.x = cvt_bf16x2_pair(f2_mul(f2_pack(__uint_as_float(r[c * 8]), __uint_as_float(r[c * 8 + 1])), inv2));
+            pk.y = cvt_bf16x2_pair(f2_mul(f2_pack(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])), inv2));
+            pk.z = cvt_bf16x2_pair(f2_mul(f2_pack(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])), inv2));
+            pk.w = cvt_bf16x2_pair(f2_mul(f2_pack(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])), inv2));
+            *reinterpret_cast<uint4*>(ob + ((uint32_t(g * (OW / 8) + c) ^ sw) << 4)) = pk;
           }
           w.arrive(B_O_DRAINED);
           pf.mark(PW_E3);
@@ -628,8 +645,8 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
 #if AVF_FUSED_PACKED
-            yk[j / 2] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[j]) + b4.x, __uint_as_float(r[j + 1]) + b4.y));
-            yk[j / 2 + 1] = gelu_bf16x2(cvt_bf16x2(__uint_as_float(r[j + 2]) + b4.z, __uint_as_float(r[j + 3]) + b4.w));
+            yk[j / 2] = gelu_bf16x2(cvt_bf16x2_pair(f2_add(f2_pack(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), f2_pack(b4.x, b4.y))));
+            yk[j / 2 + 1] = gelu_bf16x2(cvt_bf16x2_pair(f2_add(f2_pack(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), f2_pack(b4.z, b4.w))));
 #else
             yk[j / 2] = pack_bf16x2(gelu_fast(__uint_as_float(r[j]) + b4.x), gelu_fast(__uint_as_float(r[j + 1]) + b4.y));
             yk[j / 2 + 1] = pack_bf16x2(gelu_fast(__uint_as_float(r[j + 2]) + b4.z), gelu_fast(__uint_as_float(r[j + 3]) + b4.w));
