@@ -72,6 +72,7 @@ constexpr int OFF_OST = OFF_RING + (RING_HI - RING_LO) * SLOT_BYTES;   // 8 KB  
 constexpr int OFF_QRING = OFF_OST + 8192;          // QRING x 12 KB QKV weight ring; also the NCHW output staging (2 x 64 x 256 bf16 at most)
 constexpr int OFF_OUTST = OFF_QRING;
 static_assert(QRING * QSLOT_BYTES >= 2 * 64 * 256 * 2, "the NCHW output staging lives in the QKV ring");
+static_assert(QRING >= 6 && QRING < 8, "one head-full barrier per head parity needs 6 or 7 sub-slots (see qkv_producer_main)");
 constexpr int OFF_XCH = OFF_QRING + QRING * QSLOT_BYTES;               // row exchange [2][128][4] floats
 static_assert(OFF_XCH - OFF_Q == RING * SLOT_BYTES, "the nine MLP ring slots tile [OFF_Q, OFF_XCH) exactly");
 static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguous from OFF_Q");
@@ -90,7 +91,7 @@ constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, T
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
   B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_X2_FULL,
-  B_QR_FULL, B_QR_EMPTY = B_QR_FULL + QRING, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, NUM_BARS
+  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, NUM_BARS = B_G_FULL + 4
 };
 static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
 
@@ -756,25 +757,37 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
       }
     }
   };
-  auto load = [&](uint32_t s, const CUtensorMap* tm, int c0, int c1) {
+  // A wait on an mbarrier costs the waiting thread ~100 cycles even when the phase completed long ago, and the MMA thread is on
+  // the critical path of both the attention chain and the MLP.  The four 16 KB slots of one MLP GEMM therefore signal ONE "group
+  // full" barrier (armed with the 64 KB of the whole group when its first slot is issued); slots are still released one by one.
+  // Out-projection slices (one slot each) keep their per-slot barrier.  Group g uses barrier g % 4: at most three groups fit in the
+  // nine slots, and group g + 4 can only be armed after a slot of group g + 1 has been released, i.e. after the MMA thread's wait
+  // for group g.
+  uint32_t gidx = 0;
+  auto load = [&](uint32_t s, const CUtensorMap* tm, int c0, int c1, uint64_t* full_bar, uint32_t expect_bytes) {
     poll_wait(&bars[B_RING_EMPTY + s], ((pbits >> s) & 1u) ^ 1u);
     pbits ^= 1u << s;
-    mbar_expect_tx(&bars[B_RING_FULL + s], SLOT_BYTES);
-    tma_load_2d(smem + slot_offset(s), tm, &bars[B_RING_FULL + s], c0, c1);
+    if (expect_bytes != 0) mbar_expect_tx(full_bar, expect_bytes);
+    tma_load_2d(smem + slot_offset(s), tm, full_bar, c0, c1);
     ++it;
   };
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
-      for (int h = 0; h < HEADS; ++h) load(RING_LO + h % (RING_HI - RING_LO), &L.tm_out, h * DH, 0);   // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
+      for (int h = 0; h < HEADS; ++h) {                        // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
+        const uint32_t s = RING_LO + h % (RING_HI - RING_LO);
+        load(s, &L.tm_out, h * DH, 0, &bars[B_RING_FULL + s], SLOT_BYTES);
+      }
       poll_wait(&bars[B_QKV_FREE], (n_gate++) & 1);          // the attention MMAs are done with the Q/K/V staging and A1 = slots 0-1, 5-8
       uint32_t m = 0;
       auto ff1 = [&](int c) {
-        for (int kp = 0; kp < 4; ++kp) load((m++) % RING, &L.tm_w1, kp * 64, c * 128);
+        uint64_t* gb = &bars[B_G_FULL + (gidx++ & 3u)];
+        for (int kp = 0; kp < 4; ++kp) load((m++) % RING, &L.tm_w1, kp * 64, c * 128, gb, kp == 0 ? 4 * SLOT_BYTES : 0);
       };
       auto ff2 = [&](int c) {
+        uint64_t* gb = &bars[B_G_FULL + (gidx++ & 3u)];
         for (int kp = 0; kp < 2; ++kp)
-          for (int nh = 0; nh < 2; ++nh) load((m++) % RING, &L.tm_w2, c * 128 + kp * 64, nh * 128);
+          for (int nh = 0; nh < 2; ++nh) load((m++) % RING, &L.tm_w2, c * 128 + kp * 64, nh * 128, gb, (kp | nh) == 0 ? 4 * SLOT_BYTES : 0);
       };
       ff1(0);
       if (a.n_chunks > 1) ff1(1);
@@ -791,7 +804,7 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
 // ---------------------------------------------------------------------------------------------
 template <int IO>
 __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
-  uint32_t qit = 0, n_free = 0, n_read = 0;
+  uint32_t qit = 0, hq = 0, n_free = 0, n_read = 0;
   bool first = true;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     // A1 doubles as the NCHW output staging: the previous tile's bulk store must have read it (signalled after this tile's input sweep)
@@ -800,16 +813,20 @@ __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* b
       const LayerArgs& L = a.layer[l];
       if (!first) mbar_wait(&bars[B_A1_FREE], (n_free++) & 1);   // the previous layer's MLP weights (ring slots 5-8 live in A1) are consumed
       first = false;
-      for (int h = 0; h < HEADS; ++h)
+      for (int h = 0; h < HEADS; ++h, ++hq) {
+        // the four panels of a head signal ONE barrier (armed with the head's 48 KB at its first panel): the MMA thread waits once
+        // per head.  Barrier hq % 2: head hq + 2 reuses sub-slots that head hq's third and fourth panel occupied, so it is armed
+        // only after the MMA thread's wait for head hq.
+        uint64_t* fb = &bars[B_QG_FULL + (hq & 1u)];
         for (int kp = 0; kp < 4; ++kp) {
           const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
           mbar_wait(&bars[B_QR_EMPTY + s], ph ^ 1);
-          uint64_t* fb = &bars[B_QR_FULL + s];
           uint8_t* d = smem + OFF_QRING + s * QSLOT_BYTES;
-          mbar_expect_tx(fb, QSLOT_BYTES);
+          if (kp == 0) mbar_expect_tx(fb, 4 * QSLOT_BYTES);
           for (int s3 = 0; s3 < 3; ++s3) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
           ++qit;
         }
+      }
     }
   }
 }
@@ -827,28 +844,36 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   const int kmax = 128;                        // S / P span the whole tile: sequences sit in power-of-two row slots
   const uint32_t id_qkv = make_idesc_bf16(128, 96), id_s = make_idesc_bf16(128, kmax), id_pv = make_idesc_bf16(128, DH, 0, 1),
                  id_128 = make_idesc_bf16(128, 128), id_256 = make_idesc_bf16(128, 256);
-  uint32_t cbits = 0, m = 0, qit = 0, n_a0 = 0, n_hready[2] = {0, 0};
+  uint32_t obits = 0, m = 0, qit = 0, hq = 0, gidx = 0, n_a0 = 0, n_hready[2] = {0, 0};
   Prof pf;
   pf.start(blockIdx.x == 0 && leader);
   int ring_phase = PM_QKV;
-  auto slot_wait = [&](uint32_t s) -> uint32_t {     // same slot sequence as producer_main
+  auto slot_wait = [&](uint32_t s) -> uint32_t {     // an out-projection slice: its own barrier (same slot sequence as producer_main)
     pf.mark(ring_phase);
-    mbar_wait(&bars[B_RING_FULL + s], (cbits >> s) & 1u);
+    mbar_wait(&bars[B_RING_FULL + s], (obits >> s) & 1u);
+    obits ^= 1u << s;
     tc_fence_after();
-    pf.mark(ring_phase == PM_OUT ? PM_RW_OUT : (ring_phase == PM_FF1 ? PM_RW_FF1 : PM_RW_FF2));
+    pf.mark(PM_RW_OUT);
     return smem0 + uint32_t(slot_offset(s));
+  };
+  auto group_wait = [&]() {                          // the four slots of the next MLP GEMM: one barrier (see producer_main)
+    pf.mark(ring_phase);
+    mbar_wait(&bars[B_G_FULL + (gidx & 3u)], (gidx >> 2) & 1u);
+    ++gidx;
+    tc_fence_after();
+    pf.mark(ring_phase == PM_FF1 ? PM_RW_FF1 : PM_RW_FF2);
   };
   auto slot_release = [&](uint32_t s) {
     if (leader) umma_commit(&bars[B_RING_EMPTY + s]);
-    cbits ^= 1u << s;
   };
   auto qkv = [&]() {                          // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T, weights from the QKV ring
+    pf.mark(ring_phase);
+    mbar_wait(&bars[B_QG_FULL + (hq & 1u)], (hq >> 1) & 1u);      // all four panels of the head
+    ++hq;
+    tc_fence_after();
+    pf.mark(PM_RW_QKV);
     for (int kp = 0; kp < 4; ++kp) {
-      const uint32_t s = qit % QRING, ph = (qit / QRING) & 1;
-      pf.mark(ring_phase);
-      mbar_wait(&bars[B_QR_FULL + s], ph);
-      tc_fence_after();
-      pf.mark(PM_RW_QKV);
+      const uint32_t s = qit % QRING;
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(qring + s * QSLOT_BYTES);
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
@@ -867,8 +892,9 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   bool last_layer = false;
   auto ff1 = [&](int c) {                     // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
     const uint32_t d = tmem + ((c & 1) ? TM_H1 : TM_H0);
+    group_wait();
     for (int kp = 0; kp < 4; ++kp) {
-      const uint32_t s = (m++) % RING, sb = slot_wait(s);
+      const uint32_t s = (m++) % RING, sb = smem0 + uint32_t(slot_offset(s));
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
       for (int k = 0; k < 4; ++k) if (leader) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (kp | k) != 0 ? 1u : 0u);
@@ -940,9 +966,10 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         tc_fence_after();
         pf.mark(PM_WAIT_H);
         ring_phase = PM_FF2;
+        group_wait();
         for (int kp = 0; kp < 2; ++kp)        // x += gelu(H_c) W2[:, c*128..]^T
           for (int nh = 0; nh < 2; ++nh) {
-            const uint32_t s = (m++) % RING, sb = slot_wait(s);
+            const uint32_t s = (m++) % RING, sb = smem0 + uint32_t(slot_offset(s));
             const uint32_t ta = tmem + (b ? TM_H1 : TM_H0) + uint32_t(kp * 64);       // gelu(H_c) as bf16, 8 columns per 16-wide k-step
             const uint64_t db = make_desc_sw128_kmajor(sb);
 #pragma unroll
