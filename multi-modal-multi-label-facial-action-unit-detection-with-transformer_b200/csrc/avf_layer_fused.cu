@@ -39,6 +39,9 @@ using namespace fused;
 #ifndef AVF_PROD_POLL
 #define AVF_PROD_POLL 2
 #endif
+#ifndef AVF_PROD_FASTPATH
+#define AVF_PROD_FASTPATH 1
+#endif
 
 constexpr int DIM = 256, HEADS = 8, DH = 32;
 constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
@@ -61,6 +64,12 @@ constexpr int RING = 9, RING_LO = 2, RING_HI = 4, SLOT_BYTES = 16384;
 #define AVF_QRING 6
 #endif
 constexpr int QRING = AVF_QRING, QSLOT_BYTES = 12288;
+// MLP weight slots per "group full" barrier: 4 = one barrier per GEMM, 2 = one per half GEMM (the first MMAs start one slot pair earlier)
+#ifndef AVF_MLP_GROUP
+#define AVF_MLP_GROUP 4
+#endif
+constexpr int MLPG = AVF_MLP_GROUP;
+static_assert(MLPG == 2 || MLPG == 4, "MLP group size");
 
 // shared memory map (offsets from a 1024-byte aligned base)
 constexpr int OFF_A0 = 0;                          // 64 KB  LN output [128 x 256] bf16, 4 K-panels; also the NCHW input staging
@@ -91,7 +100,7 @@ constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, T
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
   B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_X2_FULL,
-  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, NUM_BARS = B_G_FULL + 4
+  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, NUM_BARS = B_G_FULL + 8
 };
 static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
 
@@ -738,6 +747,11 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
   // slots 2-4, the MLP weights over all five — slots 0-1 alias the Q/K/V staging and are only loaded after the attention MMAs).
   uint32_t pbits = 0, n_gate = 0;
   auto poll_wait = [&](uint64_t* bar, uint32_t parity) {
+#if AVF_PROD_FASTPATH
+    // Fast path first: in the MLP phase this thread issues a 16 KB slot per ~250 tensor cycles, and every probe (of the slot's
+    // barrier or of the input buffer's) costs it ~100 cycles.  The input loader is polled only while the slot is not free yet.
+    if (mbar_try_wait(bar, parity)) return;
+#endif
     poll_loader();
     const long long t0 = clock64();
 #if AVF_PROD_POLL == 1
@@ -760,9 +774,9 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
   // A wait on an mbarrier costs the waiting thread ~100 cycles even when the phase completed long ago, and the MMA thread is on
   // the critical path of both the attention chain and the MLP.  The four 16 KB slots of one MLP GEMM therefore signal ONE "group
   // full" barrier (armed with the 64 KB of the whole group when its first slot is issued); slots are still released one by one.
-  // Out-projection slices (one slot each) keep their per-slot barrier.  Group g uses barrier g % 4: at most three groups fit in the
-  // nine slots, and group g + 4 can only be armed after a slot of group g + 1 has been released, i.e. after the MMA thread's wait
-  // for group g.
+  // Out-projection slices (one slot each) keep their per-slot barrier.  Group g uses barrier g % 8: at most five groups (of two
+  // slots) fit in the nine slots, and group g + 8 can only be armed after slots of later groups have been released, i.e. after the
+  // MMA thread's wait for group g.
   uint32_t gidx = 0;
   auto load = [&](uint32_t s, const CUtensorMap* tm, int c0, int c1, uint64_t* full_bar, uint32_t expect_bytes) {
     poll_wait(&bars[B_RING_EMPTY + s], ((pbits >> s) & 1u) ^ 1u);
@@ -781,13 +795,17 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
       poll_wait(&bars[B_QKV_FREE], (n_gate++) & 1);          // the attention MMAs are done with the Q/K/V staging and A1 = slots 0-1, 5-8
       uint32_t m = 0;
       auto ff1 = [&](int c) {
-        uint64_t* gb = &bars[B_G_FULL + (gidx++ & 3u)];
-        for (int kp = 0; kp < 4; ++kp) load((m++) % RING, &L.tm_w1, kp * 64, c * 128, gb, kp == 0 ? 4 * SLOT_BYTES : 0);
+        for (int kp = 0; kp < 4; ++kp) {
+          if (kp % MLPG == 0) ++gidx;
+          load((m++) % RING, &L.tm_w1, kp * 64, c * 128, &bars[B_G_FULL + ((gidx - 1) & 7u)], kp % MLPG == 0 ? MLPG * SLOT_BYTES : 0);
+        }
       };
       auto ff2 = [&](int c) {
-        uint64_t* gb = &bars[B_G_FULL + (gidx++ & 3u)];
-        for (int kp = 0; kp < 2; ++kp)
-          for (int nh = 0; nh < 2; ++nh) load((m++) % RING, &L.tm_w2, c * 128 + kp * 64, nh * 128, gb, (kp | nh) == 0 ? 4 * SLOT_BYTES : 0);
+        for (int i = 0; i < 4; ++i) {
+          const int kp = i >> 1, nh = i & 1;
+          if (i % MLPG == 0) ++gidx;
+          load((m++) % RING, &L.tm_w2, c * 128 + kp * 64, nh * 128, &bars[B_G_FULL + ((gidx - 1) & 7u)], i % MLPG == 0 ? MLPG * SLOT_BYTES : 0);
+        }
       };
       ff1(0);
       if (a.n_chunks > 1) ff1(1);
@@ -856,9 +874,9 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     pf.mark(PM_RW_OUT);
     return smem0 + uint32_t(slot_offset(s));
   };
-  auto group_wait = [&]() {                          // the four slots of the next MLP GEMM: one barrier (see producer_main)
+  auto group_wait = [&]() {                          // the next MLPG slots of an MLP GEMM: one barrier (see producer_main)
     pf.mark(ring_phase);
-    mbar_wait(&bars[B_G_FULL + (gidx & 3u)], (gidx >> 2) & 1u);
+    mbar_wait(&bars[B_G_FULL + (gidx & 7u)], (gidx >> 3) & 1u);
     ++gidx;
     tc_fence_after();
     pf.mark(ring_phase == PM_FF1 ? PM_RW_FF1 : PM_RW_FF2);
@@ -892,8 +910,8 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   bool last_layer = false;
   auto ff1 = [&](int c) {                     // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
     const uint32_t d = tmem + ((c & 1) ? TM_H1 : TM_H0);
-    group_wait();
     for (int kp = 0; kp < 4; ++kp) {
+      if (kp % MLPG == 0) group_wait();
       const uint32_t s = (m++) % RING, sb = smem0 + uint32_t(slot_offset(s));
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
@@ -966,9 +984,9 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
         tc_fence_after();
         pf.mark(PM_WAIT_H);
         ring_phase = PM_FF2;
-        group_wait();
         for (int kp = 0; kp < 2; ++kp)        // x += gelu(H_c) W2[:, c*128..]^T
           for (int nh = 0; nh < 2; ++nh) {
+            if ((kp * 2 + nh) % MLPG == 0) group_wait();
             const uint32_t s = (m++) % RING, sb = smem0 + uint32_t(slot_offset(s));
             const uint32_t ta = tmem + (b ? TM_H1 : TM_H0) + uint32_t(kp * 64);       // gelu(H_c) as bf16, 8 columns per 16-wide k-step
             const uint64_t db = make_desc_sw128_kmajor(sb);
