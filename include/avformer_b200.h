@@ -99,6 +99,9 @@ int         avf_debug_fused_prof(uint64_t* out64, int reset);
 /* Developer aid: `host_mapped_words` = 4 uint32 in pinned (device-visible) host memory, or NULL.  A wait inside the fused
  * kernel that times out (a protocol bug) writes {block, thread, barrier index, parity} there before it traps. */
 int         avf_debug_set_trap_buffer(void* host_mapped_words);
+/* Developer aid: hits / misses of the CUtensorMap cache (maps are keyed by pointer, shape, pitch and box, so the steady state of
+ * an eagerly launched step encodes none). */
+int         avf_debug_tmap_cache(uint64_t* hits, uint64_t* misses);
 /* Developer aid: 16 %globaltimer stamps (ns) of CTA 0 of the last tcgen05 GEMM launch when the library is built with
  * -DAVF_GEMM_PROF (tools/gemm_phases.py); AVF_EUNSUPPORTED otherwise. */
 int         avf_debug_gemm_prof(uint64_t* out16);
@@ -167,6 +170,14 @@ int avf_au_former_front_fwd(int mode, const float* emb, int32_t ld_emb,
                             const void* w_cat, const float* b_cat, const float* pos, float* x,
                             int32_t n_clips, int32_t in_dim, int32_t emb_dim,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* The same front for any number of tokens per clip: BatchNorm1d (running statistics) -> n_tok stacked Linear(in_dim, emb_dim) ->
+ * view [n_clips*n_tok, emb_dim] -> + pos[n_tok, emb_dim].  n_tok = 12 is the AU_former above; n_tok = 2 is VA_former
+ * (models/heads.py:341-372: VA_BN1, VA_linear_p1..2). */
+int avf_token_front_fwd(int mode, const float* emb, int32_t ld_emb,
+                        const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                        const void* w_cat, const float* b_cat, const float* pos, float* x,
+                        int32_t n_clips, int32_t in_dim, int32_t emb_dim, int32_t n_tok,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a9 tail + a11 + a12 -------------------------------------------------------------------- */
 /* logits[c,i] = <x[c*12+i, :], w_last[i, :]>  written to out21 [n_clips, 21] (cols 12..20 zeroed,

@@ -76,6 +76,8 @@ SIGNATURES = {
     "avf_tformer_cls_extract": (ctypes.c_int, [_c_p, _c_p, _i32, _i32, _i32, _c_p]),
     "avf_au_former_front_fwd": (ctypes.c_int, [ctypes.c_int, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32,
                                                _c_p, _sz, _c_p]),
+    "avf_token_front_fwd": (ctypes.c_int, [ctypes.c_int, _c_p, _i32, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _i32, _i32, _i32, _i32,
+                                           _c_p, _sz, _c_p]),
     "avf_au_logits_fwd": (ctypes.c_int, [_c_p, _i32, _c_p, _c_p, _c_p, _i32, _i32, _c_p]),
     "avf_au_bce_loss": (ctypes.c_int, [_c_p, _i32, _c_p, _c_p, _c_p, _c_p, _i32, _c_p]),
     "avf_au_confusion_update": (ctypes.c_int, [_c_p, _i32, ctypes.c_float, _c_p, _i32, ctypes.c_float, _c_p, _i32, _c_p]),
@@ -97,6 +99,7 @@ SIGNATURES = {
     "avf_set_pdl_enabled": (ctypes.c_int, [ctypes.c_int]),
     "avf_debug_set_trap_buffer": (ctypes.c_int, [_c_p]),
     "avf_debug_gemm_prof": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
+    "avf_debug_tmap_cache": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "avf_colsum_workspace_bytes": (_sz, [_i32, _i32]),
     "avf_colsum": (ctypes.c_int, [ctypes.c_int, _c_p, _sz, _i32, _i32, _c_p, _c_p, _sz, _c_p]),
     "avf_layernorm_bwd_workspace_bytes": (_sz, [_i32, _i32]),

@@ -91,7 +91,7 @@ static EncoderWs carve_encoder_ws(const avf_stack_shape* s, int mode, void* base
 static int check_shape(const avf_stack_shape* s) {
   AVF_REQUIRE(s != nullptr, AVF_EINVAL, "null stack shape");
   AVF_REQUIRE(s->n_seq > 0 && s->n_tok > 0 && s->depth > 0, AVF_EINVAL, "empty stack: n_seq=%d n_tok=%d depth=%d", s->n_seq, s->n_tok, s->depth);
-  AVF_REQUIRE(s->dim % 128 == 0 && s->dim <= 1024, AVF_EUNSUPPORTED, "dim=%d must be a multiple of 128 (<= 1024)", s->dim);
+  AVF_REQUIRE(s->dim % 128 == 0 && s->dim <= 1536, AVF_EUNSUPPORTED, "dim=%d must be a multiple of 128 (<= 1536)", s->dim);
   AVF_REQUIRE(s->dim_head == 32 || s->dim_head == 64, AVF_EUNSUPPORTED, "dim_head=%d (supported: 32, 64)", s->dim_head);
   AVF_REQUIRE((s->heads * s->dim_head) % 64 == 0 && s->mlp_dim % 64 == 0, AVF_EUNSUPPORTED, "inner=%d / mlp=%d must be multiples of 64", s->heads * s->dim_head, s->mlp_dim);
   AVF_REQUIRE(s->n_tok <= 64, AVF_EUNSUPPORTED, "n_tok=%d: sequences longer than 64 tokens are not part of this path", s->n_tok);
@@ -163,6 +163,12 @@ int avf_encoder_fused_supported(const avf_stack_shape* s, int mode) {
 
 /* Debug: per-phase cycle counters of the fused encoder kernel (library built with -DAVF_FUSED_PROF); else AVF_EUNSUPPORTED. */
 int avf_debug_fused_prof(uint64_t* out64, int reset) { return fused_prof_read(reinterpret_cast<unsigned long long*>(out64), reset); }
+
+int avf_debug_tmap_cache(uint64_t* hits, uint64_t* misses) {
+  if (hits == nullptr || misses == nullptr) return AVF_EINVAL;
+  tmap_cache_stats(hits, misses);
+  return 0;
+}
 
 int avf_debug_gemm_prof(uint64_t* out16) { return gemm_prof_read(reinterpret_cast<unsigned long long*>(out16)); }
 
@@ -322,20 +328,27 @@ int avf_tformer_cls_extract(const float* x, float* cls, int32_t n_clips, int32_t
   return rows_gather(x, size_t(n_tok) * dim, cls, n_clips, dim, static_cast<cudaStream_t>(stream));
 }
 
-int avf_au_former_front_fwd(int mode, const float* emb, int32_t ld_emb, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
-                            const float* bn_var, const void* w_cat, const float* b_cat, const float* pos, float* x, int32_t n_clips,
-                            int32_t in_dim, int32_t emb_dim, void* workspace, size_t workspace_bytes, void* stream) {
+int avf_token_front_fwd(int mode, const float* emb, int32_t ld_emb, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                        const float* bn_var, const void* w_cat, const float* b_cat, const float* pos, float* x, int32_t n_clips,
+                        int32_t in_dim, int32_t emb_dim, int32_t n_tok, void* workspace, size_t workspace_bytes, void* stream) {
   int e = require_device();
   if (e) return e;
-  AVF_REQUIRE(emb && bn_gamma && bn_beta && bn_mean && bn_var && w_cat && b_cat && pos && x && workspace, AVF_EINVAL, "au_former_front: null pointer");
-  AVF_REQUIRE(n_clips > 0 && in_dim > 0 && emb_dim > 0, AVF_EINVAL, "au_former_front: n_clips=%d", n_clips);
+  AVF_REQUIRE(emb && bn_gamma && bn_beta && bn_mean && bn_var && w_cat && b_cat && pos && x && workspace, AVF_EINVAL, "token_front: null pointer");
+  AVF_REQUIRE(n_clips > 0 && in_dim > 0 && emb_dim > 0 && n_tok > 0, AVF_EINVAL, "token_front: n_clips=%d n_tok=%d", n_clips, n_tok);
   const size_t need = align_up(size_t(n_clips) * in_dim * elt(mode));
   AVF_REQUIRE(workspace_bytes >= need, AVF_EWORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((e = bn_rows(mode, emb, ld_emb, bn_gamma, bn_beta, bn_mean, bn_var, workspace, n_clips, in_dim, st))) return e;
-  // [n_clips, 12*emb_dim] row-major IS [n_clips*12, emb_dim]: token i = AU_linear_p{i+1}  (models/heads.py:294-319)
-  if ((e = linear(mode, workspace, in_dim, w_cat, b_cat, nullptr, 0, x, 12 * emb_dim, AVF_FP32, n_clips, 12 * emb_dim, in_dim, AVF_EPI_BIAS, st))) return e;
-  return add_row_periodic(x, emb_dim, pos, n_clips * 12, emb_dim, 12, st);
+  // [n_clips, n_tok*emb_dim] row-major IS [n_clips*n_tok, emb_dim]: token i = the i-th stacked projection  (models/heads.py:294-319, 356-364)
+  if ((e = linear(mode, workspace, in_dim, w_cat, b_cat, nullptr, 0, x, n_tok * emb_dim, AVF_FP32, n_clips, n_tok * emb_dim, in_dim, AVF_EPI_BIAS, st))) return e;
+  return add_row_periodic(x, emb_dim, pos, n_clips * n_tok, emb_dim, n_tok, st);
+}
+
+int avf_au_former_front_fwd(int mode, const float* emb, int32_t ld_emb, const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                            const float* bn_var, const void* w_cat, const float* b_cat, const float* pos, float* x, int32_t n_clips,
+                            int32_t in_dim, int32_t emb_dim, void* workspace, size_t workspace_bytes, void* stream) {
+  return avf_token_front_fwd(mode, emb, ld_emb, bn_gamma, bn_beta, bn_mean, bn_var, w_cat, b_cat, pos, x, n_clips, in_dim, emb_dim, 12, workspace,
+                             workspace_bytes, stream);
 }
 
 int avf_au_logits_fwd(const float* x, int32_t ld_x, const float* w_last, float* out21, int32_t* decisions, int32_t n_clips, int32_t dim, void* stream) {

@@ -18,6 +18,9 @@
 // the latter split along R over CTAs (deterministic partial tiles + a reduction kernel).
 #include <cuda.h>
 
+#include <atomic>
+#include <unordered_map>
+
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -404,7 +407,56 @@ EncodeTiledFn get_encode_fn() {
 
 // 2-D bf16 row-major [rows, cols] (row stride ld elements), box = [box_rows x box_cols]: 64 cols with the 128B swizzle
 // (default) or 32 cols with the 64B swizzle.
+// A tensor map is a pure function of (pointer, shape, pitch, box): encoded maps are kept in a small per-thread cache keyed by exactly
+// those values ("cached CUtensorMaps keyed by pointer/shape"), so the steady state of an eagerly launched
+// step — the same activations and weights every iteration — costs a hash lookup per operand instead of a driver call
+// (cuTensorMapEncodeTiled, ~1 us; two per GEMM launch, four per layer of a fused launch).  The map holds no reference to the memory:
+// a freed and re-allocated buffer with the same address, shape and pitch yields the same, still correct, map.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  uint64_t rows, cols, ld;
+  uint32_t box_rows, box_cols;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows * 0xBF58476D1CE4E5B9ull) ^ (k.cols << 21) ^ (k.ld << 42) ^ (uint64_t(k.box_rows) << 7) ^ k.box_cols;
+    return size_t(h ^ (h >> 29));
+  }
+};
+constexpr size_t TMAP_CACHE_MAX = 4096;      // ~600 KB at most; cleared wholesale when full (a training step touches a few hundred)
+std::atomic<uint64_t> g_tmap_hits{0}, g_tmap_misses{0};
+}  // namespace
+
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  *hits = g_tmap_hits.load();
+  *misses = g_tmap_misses.load();
+}
+
+static int encode_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = 64) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{ptr, rows, cols, ld, box_rows, box_cols};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *tm = it->second;
+    g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  const int e = encode_tmap_bf16_2d(tm, ptr, rows, cols, ld, box_rows, box_cols);
+  if (e) return e;
+  if (cache.size() >= TMAP_CACHE_MAX) cache.clear();
+  cache.emplace(key, *tm);
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+static int encode_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();
   AVF_REQUIRE(fn != nullptr, AVF_ENODEVICE, "cuTensorMapEncodeTiled is not available from the driver");
   AVF_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, AVF_EINVAL,

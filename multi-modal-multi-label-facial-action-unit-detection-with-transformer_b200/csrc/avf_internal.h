@@ -72,6 +72,7 @@ int gemm_umma(int trans_a, int trans_b, const void* a, int lda, const void* w, i
               const void* aux, int ld_aux, void* c, int ldc, int c_mode, int m, int n, int k, int flags, void* ws, size_t ws_bytes,
               cudaStream_t stream, DropSpec drop = DropSpec{});
 size_t gemm_umma_workspace_bytes(int m, int n, int k);
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses);     // CUtensorMap cache (keyed by pointer / shape / pitch / box)
 int gemm_prof_read(unsigned long long* out16);               // milestone timestamps of CTA 0, only with -DAVF_GEMM_PROF
 int linear_umma(const void* a, int lda, const void* w, const float* bias, const float* res, int ld_res, void* c, int ldc,
                 int c_mode, int m, int n, int k, int flags, cudaStream_t st);

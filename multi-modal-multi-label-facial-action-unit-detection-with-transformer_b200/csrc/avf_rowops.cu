@@ -10,7 +10,7 @@ namespace avf {
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row kept in registers (dim <= 1024, dim % 128 == 0)
+// LayerNorm: one warp per row, row kept in registers (dim <= 1536, dim % 128 == 0; 1536 = the TFormer of models/tformer.py:301)
 // nn.LayerNorm(dim) of PreNorm, models/heads.py:178-185 (biased variance, eps = 1e-5)
 // ---------------------------------------------------------------------------------------------
 template <typename OutT, int VEC>   // VEC float4 per lane: dim = 128 * VEC
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) au_confusion_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 int layernorm(int out_mode, const float* x, int ld_x, const float* g, const float* b, void* y, int rows, int dim, cudaStream_t st) {
   AVF_REQUIRE(rows > 0, AVF_EINVAL, "layernorm: rows=%d", rows);
-  AVF_REQUIRE(dim % 128 == 0 && dim <= 1024 && ld_x % 4 == 0, AVF_EUNSUPPORTED, "layernorm: dim=%d must be a multiple of 128, <= 1024", dim);
+  AVF_REQUIRE(dim % 128 == 0 && dim <= 1536 && ld_x % 4 == 0, AVF_EUNSUPPORTED, "layernorm: dim=%d must be a multiple of 128, <= 1536", dim);
   const int wpb = 8;
   dim3 grid(ceil_div(rows, wpb)), block(wpb * 32);
 #define AVF_LN(V)                                                                                                   \
@@ -355,7 +355,7 @@ int layernorm(int out_mode, const float* x, int ld_x, const float* g, const floa
     else launch_pdl(layernorm_kernel<float, V>, grid, block, 0, st, x, ld_x, g, b, static_cast<float*>(y), rows);             \
     break;
   switch (dim / 128) {
-    AVF_LN(1) AVF_LN(2) AVF_LN(3) AVF_LN(4) AVF_LN(5) AVF_LN(6) AVF_LN(7) AVF_LN(8)
+    AVF_LN(1) AVF_LN(2) AVF_LN(3) AVF_LN(4) AVF_LN(5) AVF_LN(6) AVF_LN(7) AVF_LN(8) AVF_LN(9) AVF_LN(10) AVF_LN(11) AVF_LN(12)
   }
 #undef AVF_LN
   AVF_LAUNCH_CHECK("layernorm_kernel");

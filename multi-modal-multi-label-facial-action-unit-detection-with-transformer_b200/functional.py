@@ -247,6 +247,21 @@ def au_former_front(emb: torch.Tensor, ld_emb: int, n_clips: int, bn: Sequence[t
     return x
 
 
+def token_front(emb: torch.Tensor, ld_emb: int, n_clips: int, n_tok: int, bn: Sequence[torch.Tensor], w_cat: torch.Tensor, b_cat: torch.Tensor,
+                pos: torch.Tensor, mode: int) -> torch.Tensor:
+    """au_former_front for any token count: BN(eval) + n_tok stacked Linear + pos -> fp32 tokens [n_clips*n_tok, emb_dim]
+    (n_tok = 2: VA_former, models/heads.py:354-364)."""
+    _cuda(emb, "emb")
+    in_dim, emb_dim = w_cat.shape[1], w_cat.shape[0] // n_tok
+    x = torch.empty((n_clips * n_tok, emb_dim), dtype=torch.float32, device=emb.device)
+    ws = workspace(n_clips * in_dim * 4 + 256, emb.device)
+    g, b, mu, var = (_f32c(t) for t in bn)
+    check(_lib.lib().avf_token_front_fwd(mode, _ptr(emb), ld_emb, _ptr(g), _ptr(b), _ptr(mu), _ptr(var), _ptr(w_cat), _ptr(b_cat),
+                                         _ptr(_f32c(pos)), _ptr(x), n_clips, in_dim, emb_dim, n_tok, _ptr(ws), ws.numel(), _stream()),
+          "token_front_fwd")
+    return x
+
+
 def au_logits(x: torch.Tensor, w_last: torch.Tensor, n_clips: int, want_decisions: bool = False):
     """Tail of the fusion head: [B,21] zero-padded output (+ int32 decisions)."""
     _cuda(x, "x")

@@ -151,3 +151,42 @@ class former_AU_head(nn.Module):
 
 
 tformer_AU_head = former_AU_head     # the name the class carries in models/tformer.py:362
+
+
+class VA_former(nn.Module):
+    """VA_former(input_dim=512, emb_dim=128, dropout=0.0) (models/heads.py:341-372): BatchNorm1d -> 2 x Linear(512,128) -> 2 tokens + pos
+    -> Transformer(128, depth 2, 8 x 32, mlp 128) -> 2 x Linear(128,1) -> (VA_out [B,2], tokens [B,2,128]).  One more (N, D, I, M) =
+    (2, 128, 256, 128) instantiation of the stack the AU path uses; inference kernels only."""
+
+    def __init__(self, input_dim=512, emb_dim=128, dropout=0.0):
+        super().__init__()
+        self.emb_dim = input_dim
+        self.VA_BN1 = nn.BatchNorm1d(input_dim)
+        self.VA_linear_p1 = nn.Linear(input_dim, emb_dim)
+        self.VA_linear_p2 = nn.Linear(input_dim, emb_dim)
+        self.pos_embedding = nn.Parameter(torch.randn(1, 2, emb_dim))
+        self.corr_transformer = Transformer(emb_dim, depth=2, heads=8, mlp_dim=128, dim_head=32, dropout=dropout)
+        self.VA_linear_last1 = nn.Linear(emb_dim, 1, bias=False)
+        self.VA_linear_last2 = nn.Linear(emb_dim, 1, bias=False)
+        self._front: Optional[_PackedFront] = None
+
+    def _packed_front(self):
+        mode = AF._mode(self.corr_transformer.precision or default_precision())
+        if self._front is None or self._front.mode != mode or self._front.stale():
+            self._front = _PackedFront([self.VA_linear_p1, self.VA_linear_p2], mode)
+        return self._front
+
+    @torch.no_grad()
+    def forward(self, emb):
+        AF._cuda(emb, "emb")
+        if self.training:
+            raise RuntimeError("VA_former: only the inference kernels are instantiated for this variant; call .eval()")
+        bs = emb.shape[0]
+        emb = emb.detach().float().contiguous()
+        f = self._packed_front()
+        bn = self.VA_BN1
+        x = AF.token_front(emb, emb.shape[1], bs, 2, (bn.weight, bn.bias, bn.running_mean, bn.running_var), f.w, f.b, self.pos_embedding[0], f.mode)
+        tok = self.corr_transformer.forward_(x, bs, 2).view(bs, 2, -1)
+        w = torch.stack([self.VA_linear_last1.weight[0], self.VA_linear_last2.weight[0]]).float()       # [2, emb]
+        va_out = (tok * w.unsqueeze(0)).sum(-1)      # two 128-wide dots per clip: output glue, not a kernel of the path
+        return va_out, tok

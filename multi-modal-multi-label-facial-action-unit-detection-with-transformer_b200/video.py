@@ -106,6 +106,26 @@ class ResFormer(nn.Module):
         return torch.flatten(self.avgpool(self.layer4(fmap)), 1)
 
 
+class SFormerBlock(nn.Module):
+    """The spatial-transformer region alone, for any channel width: pos_embedding[1, num_patches, dim] + Transformer over the
+    H*W positions of an NCHW map, transposed back (models/vformer.py:245-259).  ResFormer above is the dim-256 instantiation on the hot
+    path; VGGFormer (models/vggformer.py:250-258: num_patches 49, dim 512, depth 1, 8 x 32, mlp 512) is this block behind a VGGFace2
+    trunk that is not part of this package.  Inference kernels only."""
+
+    def __init__(self, num_patches=7 * 7, dim=512, depth=1, heads=8, mlp_dim=512, dim_head=32, dropout=0.0):
+        super().__init__()
+        self.pos_embedding = nn.Parameter(torch.randn(1, num_patches, dim))
+        self.spatial_transformer = Transformer(dim, depth, heads, dim_head, mlp_dim, dropout)
+
+    @torch.no_grad()
+    def forward(self, fmap, out=None):
+        st = self.spatial_transformer
+        n_tok = fmap.shape[2] * fmap.shape[3]
+        if n_tok > self.pos_embedding.shape[1]:
+            raise ValueError(f"map has {n_tok} positions but pos_embedding holds {self.pos_embedding.shape[1]}")
+        return AF.sformer_fwd(fmap, self.pos_embedding[0, :n_tok], st.packed(), st.heads, st.dim_head, st.mlp_dim, out=out)
+
+
 class TFormer(nn.Module):
     """cls + frame tokens -> 3-layer encoder -> cls row (models/vformer.py:270-293).
     ``num_patches`` is the clip length T (the reference hard-wires 16 in VideoModel)."""

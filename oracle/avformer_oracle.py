@@ -431,6 +431,49 @@ def state_dict_spec(n_frames: int = 16):
     yield "loss_AU.loss_fn.pos_weight", (12,), "pos_weight"
 
 
+# --------------------------------------------------------------------------
+# the other instantiations of the same block
+# --------------------------------------------------------------------------
+def variant_spec(name: str, n_frames: int = 16):
+    """"tformer1536": TFormer(dim=128*12) of models/tformer.py:301 (depth 3, 8 x 64, mlp 1024);  "sformer512": the spatial transformer
+    of VGGFormer, models/vggformer.py:252-258 (49 tokens, dim 512, depth 1, 8 x 32, mlp 512);  "va_former": models/heads.py:341-353."""
+    if name == "tformer1536":
+        yield "cls_token", (1, 1, 1536), "normal"
+        yield "pos_embedding", (1, n_frames + 1, 1536), "normal"
+        yield from _encoder_spec("spatial_transformer.", 1536, 3, 512, 1024)
+    elif name == "sformer512":
+        yield "pos_embedding", (1, 49, 512), "normal"
+        yield from _encoder_spec("spatial_transformer.", 512, 1, 256, 512)
+    elif name == "va_former":
+        yield "pos_embedding", (1, 2, 128), "normal"
+        yield from _bn_spec("VA_BN1.", 512)
+        for i in (1, 2):
+            yield f"VA_linear_p{i}.weight", (128, 512), "linear_w"
+            yield f"VA_linear_p{i}.bias", (128,), ("linear_b", 512)
+        yield from _encoder_spec("corr_transformer.", 128, 2, 256, 128)
+        for i in (1, 2):
+            yield f"VA_linear_last{i}.weight", (1, 128), "linear_w"
+    else:  # pragma: no cover
+        raise ValueError(name)
+
+
+def make_variant_params(name: str, seed: int, n_frames: int = 16, dtype=torch.float32) -> P:
+    return params_from_spec(variant_spec(name, n_frames), seed, dtype)
+
+
+def va_former(emb, p: P, pre: str = ""):
+    """models/heads.py:354-372.  emb [B,512] -> BatchNorm1d (running statistics) -> 2 x Linear(512,128)+b, token i = VA_linear_p{i+1}
+    -> + pos -> 2 encoder layers (128, 8 x 32, mlp 128) -> VA_linear_last{i+1} on token i.  Returns (VA_out [B,2], tokens [B,2,128])."""
+    g, b = p[pre + "VA_BN1.weight"], p[pre + "VA_BN1.bias"]
+    mu, var = p[pre + "VA_BN1.running_mean"], p[pre + "VA_BN1.running_var"]
+    e = (emb - mu) / torch.sqrt(var + 1e-5) * g + b
+    toks = [e @ p[f"{pre}VA_linear_p{i}.weight"].t() + p[f"{pre}VA_linear_p{i}.bias"] for i in (1, 2)]
+    x = torch.stack(toks, dim=1) + p[pre + "pos_embedding"][:, :2]
+    x = transformer(x, p, pre + "corr_transformer.", 2, 8)
+    out = torch.stack([(x[:, i] * p[f"{pre}VA_linear_last{i + 1}.weight"][0]).sum(-1) for i in range(2)], dim=1)
+    return out, x
+
+
 def is_backbone_key(key: str) -> bool:
     """True for the conv-backbone entries (outside the hot path): the audio ResNet18 and the conv
     stages of ResFormer (conv1, bn1, layer1..4)."""
@@ -445,9 +488,14 @@ def make_state_dict(seed: int = 0, n_frames: int = 16, dtype=torch.float32, hot_
     pos/cls: N(0,1), conv: Kaiming-normal fan_out — SURVEY.md §8c) but non-trivial LayerNorm/BatchNorm
     affine terms and running statistics so that no fused term can hide behind an identity.
     One numpy Generator per key (seeded by (seed, index)) so a subset reproduces the same values."""
+    return params_from_spec(state_dict_spec(n_frames), seed, dtype, skip=is_backbone_key if hot_path_only else None)
+
+
+def params_from_spec(spec, seed: int, dtype=torch.float32, skip=None) -> P:
+    """Values for any (key, shape, kind) list: one numpy Generator per key, seeded by (seed, index)."""
     sd: P = {}
-    for idx, (key, shape, kind) in enumerate(state_dict_spec(n_frames)):
-        if hot_path_only and is_backbone_key(key):
+    for idx, (key, shape, kind) in enumerate(spec):
+        if skip is not None and skip(key):
             continue
         rng = np.random.default_rng([seed, idx])
         fan = kind[1] if isinstance(kind, tuple) else None

@@ -59,6 +59,30 @@ def test_encoder_stack_token_count_extremes(n_tok):
             assert _maxerr(tr(x), ref) < 6e-2
 
 
+def test_tensor_maps_are_cached_by_pointer_and_shape():
+    """The second eager launch of the same GEMM / fused stack on the same buffers encodes no new CUtensorMap."""
+    L = A._lib.lib()
+
+    def stats():
+        h, m = ctypes.c_uint64(), ctypes.c_uint64()
+        assert L.avf_debug_tmap_cache(ctypes.byref(h), ctypes.byref(m)) == 0
+        return h.value, m.value
+
+    torch.manual_seed(3)
+    tr = A.Transformer(512, 2, 8, 64, 1024).cuda().eval()
+    tr.precision = "bf16"
+    x = torch.randn(4, 17, 512, device="cuda")
+    with torch.no_grad():
+        y0 = tr(x).clone()
+        _, m0 = stats()
+        y1 = tr(x).clone()
+        h1, m1 = stats()
+        y2 = tr(x).clone()
+        h2, m2 = stats()
+    assert torch.equal(y0, y1) and torch.equal(y1, y2)
+    assert m2 == m1 and h2 > h1, (m0, m1, m2, h1, h2)
+
+
 def test_single_clip_and_all_rows_ignored():
     T, seed = 16, 31
     m = _model(seed, T, "bf16")

@@ -159,3 +159,21 @@ def test_batchnorm_train_restatement():
     rm, rv = O.bn_running_update(x, rm0, rv0)
     _close(rm, bn.running_mean, 1e-12)
     _close(rv, bn.running_var, 1e-12)
+
+
+def test_variant_instantiations_match_reference_golden(golden_dir):
+    """TFormer at dim 1536 (models/tformer.py:301), the dim-512 spatial transformer of VGGFormer
+    (models/vggformer.py:252-258) and VA_former (models/heads.py:341-372) — the oracle restatements against outputs of the reference
+    classes themselves (tests/golden/make_golden_variants.py)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_variants", os.path.join(golden_dir, "make_golden_variants.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = dict(np.load(os.path.join(golden_dir, "variants.npz")))
+    frames, fmap, emb = mg.variant_inputs()
+    cls = O.tformer(frames, O.make_variant_params("tformer1536", mg.SEED), "", 16)
+    assert np.abs(cls.numpy() - g["tformer1536_cls"]).max() < 2e-5
+    s_out = O.sformer_tokens(fmap, O.make_variant_params("sformer512", mg.SEED), "")
+    assert np.abs(s_out.numpy() - g["sformer512_out"]).max() < 2e-5
+    va_out, va_tok = O.va_former(emb, O.make_variant_params("va_former", mg.SEED))
+    assert np.abs(va_out.numpy() - g["va_out"]).max() < 1e-5 and np.abs(va_tok.numpy() - g["va_tokens"]).max() < 1e-5
