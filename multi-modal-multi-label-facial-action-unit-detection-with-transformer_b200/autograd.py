@@ -40,6 +40,27 @@ def _f32_dense(t: torch.Tensor) -> torch.Tensor:
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+def direct_grad_ok(prm) -> bool:
+    """May the kernels add this parameter's gradient straight into ``prm.grad``, bypassing autograd's AccumulateGrad?  Only when an
+    optimiser asked for it (optim.FusedAdam marks the parameters whose .grad is a view of its flat bucket with ``_avf_direct_grad``)
+    and nobody is listening on the normal path: tensor hooks and post-accumulate-grad hooks (torch DDP's reducer registers those)
+    only fire when the gradient is returned to autograd.  torch.autograd.grad() / backward(inputs=...) on such parameters still
+    see None — FusedAdam-managed parameters are meant for loss.backward() + optimizer.step(); torch DDP is not supported on
+    them (dp.SegmentReducer / FusedAdam do the reduction)."""
+    pg = prm.grad
+    if pg is None or not getattr(prm, "_avf_direct_grad", False):
+        return False
+    if pg.dtype != torch.float32 or not pg.is_cuda or not pg.is_contiguous():
+        return False
+    if getattr(prm, "_backward_hooks", None) or getattr(prm, "_post_accumulate_grad_hooks", None):
+        return False
+    return True
+
+
+def _direct_targets(params):
+    return [p.grad if direct_grad_ok(p) else None for p in params]
+
+
 def _hand_over(params, grads):
     """Gradient hand-over without one `add` launch per parameter: when every parameter that receives a gradient here already
     owns an fp32 ``.grad`` buffer of the right shape on the GPU (FusedAdam keeps them as views of its flat bucket), all the
@@ -51,7 +72,7 @@ def _hand_over(params, grads):
         if g is None:
             continue
         pg = prm.grad
-        if pg is None or pg.dtype != torch.float32 or not pg.is_cuda or pg.shape != g.shape or not g.is_cuda:
+        if not direct_grad_ok(prm) or pg.shape != g.shape or not g.is_cuda:
             return list(grads)
         dst.append(pg)
         src.append(g if g.dtype == torch.float32 else g.float())
@@ -76,7 +97,7 @@ class EncoderStackFn(torch.autograd.Function):
     def backward(ctx, dy):
         needs = ctx.needs_input_grad
         dx = _f32_dense(dy).clone()
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop, into=[p.grad for p in ctx.params])
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[4:]), *ctx.drop, into=_direct_targets(ctx.params))
         ctx.tape = None
         _notify(ctx.params)
         return (dx if needs[0] else None, None, None, None, *grads)
@@ -103,7 +124,7 @@ class SFormerFn(torch.autograd.Function):
         needs = ctx.needs_input_grad
         F_, C, H, W = ctx.fshape
         dx = AF.sformer_tokens_pack(dout, None)
-        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]), *ctx.drop, into=[p.grad for p in ctx.params])
+        dx, grads = AF.encoder_stack_bwd_(dx, ctx.packed, ctx.shape_, ctx.tape, list(needs[3:]), *ctx.drop, into=_direct_targets(ctx.params))
         ctx.tape = None
         dpos = None
         if needs[1]:

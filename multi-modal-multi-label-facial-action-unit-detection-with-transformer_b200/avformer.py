@@ -204,6 +204,8 @@ class TwoStreamAuralVisualFormer(nn.Module):
             }
         main = torch.cuda.current_stream(dev)
         cs = st["copy_stream"]
+        if st["k"] == 0:
+            cs.wait_stream(main)                               # the staging buffers were just allocated on the main stream
         cur = st["sets"][st["k"] & 1]
         st["k"] += 1
         cs.wait_event(cur["done"])                             # the kernels of the call that last used this set (no-op the first time)

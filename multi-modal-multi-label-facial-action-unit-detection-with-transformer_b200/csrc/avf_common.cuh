@@ -42,6 +42,34 @@ int sm_cap();          // avf_set_sm_cap: upper bound on the grid of the persist
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute and the SM count are per DEVICE: one-time set-up is keyed by the current device ordinal, so a process that
+// drives several GPUs configures every kernel on each of them.
+constexpr int AVF_MAX_DEVICES = 64;
+static inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % AVF_MAX_DEVICES;
+}
+struct PerDeviceOnce {
+  bool done[AVF_MAX_DEVICES] = {};
+  bool first() {                       // true exactly once per device
+    const int d = current_device_slot();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+static inline int sm_count_of_current_device() {
+  static int n[AVF_MAX_DEVICES] = {};
+  const int d = current_device_slot();
+  if (n[d] == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[d] = v;
+  }
+  return n[d];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization
 // attribute and starts with pdl_wait() (griddepcontrol.wait: blocks until the preceding grid of the stream has completed and

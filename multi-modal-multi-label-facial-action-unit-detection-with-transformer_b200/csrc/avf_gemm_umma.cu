@@ -475,14 +475,7 @@ static int encode_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, 
   return 0;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return sm_count_of_current_device(); }
 
 template <int BN, int STAGES, typename OutT, bool A_MN, bool B_MN>
 static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, int ldc, const float* bias,
@@ -496,11 +489,8 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, OutT* c, 
   e = B_MN ? make_tmap_bf16_2d(&tw, w, k, n, ldw, 64) : make_tmap_bf16_2d(&tw, w, n, k, ldw, BN);
   if (e) return e;
   auto kern = gemm_umma_kernel<BN, STAGES, OutT, A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
-    AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int n_tiles = (n / BN) * ceil_div(m, BM) * splits;
   const int cap = sm_cap();
   launch_pdl(kern, min(n_tiles, cap > 0 ? min(cap, sm_count()) : sm_count()), 384, Cfg::SMEM_BYTES, stream, ta, tw, c, ldc, bias, res, ld_res, m, n, k, flags,

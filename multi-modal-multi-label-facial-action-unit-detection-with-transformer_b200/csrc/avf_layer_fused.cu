@@ -1077,14 +1077,7 @@ bool fixed_ntok_enabled() {      // developer A/B: AVF_FUSED_FIXED_NTOK=0 keeps 
   return v != 0;
 }
 
-int sm_count_cached() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+int sm_count_cached() { return sm_count_of_current_device(); }
 
 }  // namespace
 
@@ -1148,12 +1141,11 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
     A.ln1_g = L[l].ln1_gamma; A.ln1_b = L[l].ln1_beta; A.b_out = L[l].b_out;
     A.ln2_g = L[l].ln2_gamma; A.ln2_b = L[l].ln2_beta; A.b_ff1 = L[l].b_ff1; A.b_ff2 = L[l].b_ff2;
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_NCHW_BF16, 49>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_NCHW_BF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
     AVF_CUDA(cudaFuncSetAttribute(encoder_fused_kernel<IO_ROWS_F32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-    configured = true;
   }
   const int cap = sm_cap();
   const int grid = min(a.n_tiles, cap > 0 ? min(cap, sm_count_cached()) : sm_count_cached());

@@ -384,11 +384,10 @@ int sformer_pack(int io_mode, const void* fmap, const float* pos, float* x, int 
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "sformer_tokens_pack: frame of %d x %d does not fit shared memory", dim, hw);
   AVF_REQUIRE((size_t(dim) * hw) % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15) == 0, AVF_EUNSUPPORTED,
               "sformer_tokens_pack: frames must be 16-byte aligned multiples of 8 elements (dim=%d hw=%d)", dim, hw);
-  static bool cfg = false;
-  if (!cfg) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     AVF_CUDA(cudaFuncSetAttribute(sformer_pack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVF_CUDA(cudaFuncSetAttribute(sformer_pack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
   }
   const int grid = sformer_grid(n_frames, smem);
   if (io_mode == AVF_BF16) launch_pdl(sformer_pack_kernel<__nv_bfloat16>, grid, 256, smem, st, static_cast<const __nv_bfloat16*>(fmap), pos, x, n_frames, dim, hw);
@@ -403,11 +402,10 @@ int sformer_unpack(int io_mode, const float* x, void* fmap, int n_frames, int di
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "sformer_tokens_unpack: frame of %d x %d does not fit shared memory", dim, hw);
   AVF_REQUIRE((size_t(dim) * hw) % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 15) == 0, AVF_EUNSUPPORTED,
               "sformer_tokens_unpack: frames must be 16-byte aligned multiples of 8 elements (dim=%d hw=%d)", dim, hw);
-  static bool cfg = false;
-  if (!cfg) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     AVF_CUDA(cudaFuncSetAttribute(sformer_unpack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AVF_CUDA(cudaFuncSetAttribute(sformer_unpack_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
   }
   const int grid = sformer_grid(n_frames, smem);
   if (io_mode == AVF_BF16) launch_pdl(sformer_unpack_kernel<__nv_bfloat16>, grid, 256, smem, st, x, static_cast<__nv_bfloat16*>(fmap), n_frames, dim, hw);

@@ -271,10 +271,9 @@ static int launch_attention(const void* qkv, void* out, int n_seq, int n_tok, in
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "attention: %d tokens x %d inner does not fit shared memory", n_tok, inner);
   int threads = min(kMaxThreads, ceil_div(threads_per_seq * spb, 32) * 32);
   auto kern = attention_small_kernel<T, DH>;
-  static bool cfg = false;
-  if (!cfg) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
   }
   const float scale_log2e = 1.4426950408889634f / sqrtf(float(DH));
   launch_pdl(kern, dim3(ceil_div(n_seq, spb), ceil_div(heads, hpb)), threads, smem, st, static_cast<const T*>(qkv), static_cast<T*>(out), n_seq, n_tok, heads, spb, hpb,

@@ -604,10 +604,9 @@ static int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, i
   const size_t smem = (size_t(4) * n_tok * (DH + 1) + size_t(2) * n_tok * (n_tok + 1)) * sizeof(float);
   AVF_REQUIRE(smem <= 200 * 1024, AVF_EUNSUPPORTED, "attention_bwd: %d tokens x %d do not fit shared memory", n_tok, DH);
   auto kern = attention_bwd_kernel<T, DH>;
-  static bool cfg = false;
-  if (!cfg) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     AVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
   }
   launch_pdl(kern, n_seq * heads, 128, smem, st, static_cast<const T*>(qkv), static_cast<const T*>(dout), static_cast<T*>(dqkv), n_tok, heads,
                                          rsqrtf(float(DH)));

@@ -36,6 +36,11 @@ def _io_mode(t: torch.Tensor) -> int:
 def _cuda(t: torch.Tensor, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise RuntimeError(f"avformer_b200: '{name}' is on {t.device}; the B200 path has no CPU fallback")
+    # The library launches on the CURRENT device's current stream and never switches devices itself: a tensor that lives on another
+    # GPU would be dereferenced by kernels running on the wrong device.  Fail loudly instead (use torch.cuda.device(...) / set_device).
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"avformer_b200: '{name}' is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           f"select the tensor's device first (torch.cuda.set_device / with torch.cuda.device(...))")
     return t
 
 
@@ -94,6 +99,13 @@ def fresh_bf16_image(param: torch.Tensor) -> Optional[torch.Tensor]:
     return None
 
 
+def _src_version(t: torch.Tensor) -> tuple:
+    """What identifies the VALUE of a parameter for the packed (bf16 / stacked) copies made from it: address, torch's version counter
+    (in-place edits, load_state_dict, .to()) and ``_avf_wver``, which optim.FusedAdam bumps on the parameters it updates through raw
+    pointers.  Per parameter, so a frozen sub-model's copies stay valid while an optimiser steps the rest of the model."""
+    return (t.data_ptr(), t._version, getattr(t, "_avf_wver", 0))
+
+
 class PackedStack:
     """Device-side weight table of one encoder stack: an array of avf_layer_weights plus the tensors
     that keep the pointers alive.  ``sources`` are the live nn.Parameters; ``stale()`` compares their
@@ -117,11 +129,11 @@ class PackedStack:
                         t = to_bf16(_f32c(src))
                 self.keep.append(t)
                 setattr(self.array[i], name, t.data_ptr())
-        self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.versions = [_src_version(s) for s in self.sources]
         self.epoch = WEIGHTS_EPOCH
 
     def stale(self) -> bool:
-        return self.epoch != WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != WEIGHTS_EPOCH or any(_src_version(s) != v for s, v in zip(self.sources, self.versions))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -308,7 +320,7 @@ def encoder_fused_supported(shape: StackShape, precision="bf16") -> bool:
 # ------------------------------------------------------------------------------------------------
 # training: tape forward, backward, optimiser (include/avformer_b200.h, section "training")
 # ------------------------------------------------------------------------------------------------
-WEIGHTS_EPOCH = 0          # bumped by optimisers that update parameters through raw pointers (optim.FusedAdam)
+WEIGHTS_EPOCH = 0          # global "every packed copy is stale" switch (bump_weights_epoch); FusedAdam uses the per-parameter _avf_wver instead
 
 
 def bump_weights_epoch() -> None:

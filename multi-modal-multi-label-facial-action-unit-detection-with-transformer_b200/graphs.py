@@ -27,7 +27,7 @@ def weights_signature(model) -> tuple:
     from . import functional as AF
     v = 0
     for t in list(model.parameters()) + list(model.buffers()):
-        v = (v * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        v = (v * 1000003 + (t._version + getattr(t, "_avf_wver", 0)) * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
     return (AF.WEIGHTS_EPOCH, v)
 
 

@@ -22,22 +22,22 @@ class _PackedFront:
         w = torch.cat([l.weight.detach().float() for l in linears], dim=0).contiguous()
         self.w = AF.to_bf16(w) if mode == AF.AVF_BF16 else w
         self.b = torch.cat([l.bias.detach().float() for l in linears], dim=0).contiguous()
-        self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.versions = [AF._src_version(s) for s in self.sources]
         self.epoch = AF.WEIGHTS_EPOCH
 
     def stale(self):
-        return self.epoch != AF.WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != AF.WEIGHTS_EPOCH or any(AF._src_version(s) != v for s, v in zip(self.sources, self.versions))
 
 
 class _PackedLast:
     def __init__(self, linears):
         self.sources = [l.weight for l in linears]
         self.w = torch.cat([l.weight.detach().float() for l in linears], dim=0).contiguous()     # [12, dim]
-        self.versions = [(s.data_ptr(), s._version) for s in self.sources]
+        self.versions = [AF._src_version(s) for s in self.sources]
         self.epoch = AF.WEIGHTS_EPOCH
 
     def stale(self):
-        return self.epoch != AF.WEIGHTS_EPOCH or any((s.data_ptr(), s._version) != v for s, v in zip(self.sources, self.versions))
+        return self.epoch != AF.WEIGHTS_EPOCH or any(AF._src_version(s) != v for s, v in zip(self.sources, self.versions))
 
 
 class AU_former(nn.Module):

@@ -83,6 +83,7 @@ class FusedAdam(torch.optim.Optimizer):
                 flat_g[o:o + p.numel()].copy_(p.grad.detach().reshape(-1))
                 p.data = flat_p[o:o + p.numel()].view(p.shape)
                 p.grad = flat_g[o:o + p.numel()].view(p.shape)
+                p._avf_direct_grad = True           # autograd.direct_grad_ok: the backward kernels may accumulate into this view
         shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)       # bf16 copy of the bucket, refreshed by the update kernel
         bounds, counts = [], []                                          # [lo, hi) of each non-empty segment in the bucket
         for si in range(self._n_seg + 1):
@@ -99,8 +100,52 @@ class FusedAdam(torch.optim.Optimizer):
                     seg_of[id(q)] = si
         self._seg_of = seg_of
         self._n_seg = len(bounds)
-        return dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
-                    bounds=bounds, counts=counts)
+        b = dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
+                 bounds=bounds, counts=counts)
+        # moments restored by load_state_dict before the bucket existed (torch keeps them in self.state until then)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                st = self.state.get(p)
+                if st:
+                    b["m"][o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+                    b["v"][o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+                    b["step"] = max(b["step"], int(st["step"]))
+                    self.state.pop(p)
+        return b
+
+    # -- checkpointing: torch.optim.Adam's state layout (step / exp_avg / exp_avg_sq per parameter) ------------------------------
+    def state_dict(self):
+        """The moments live in the flat buckets; expose them per parameter in torch.optim.Adam's format so that a resumed run
+        continues with the same exp_avg / exp_avg_sq / bias-correction step (train.py saves only the model, but a runner that
+        checkpoints the optimiser must not silently restart the moments)."""
+        for b in self._buckets:
+            if b is None:
+                continue
+            for p, o in zip(b["params"], b["offs"]):
+                n = p.numel()
+                self.state[p] = {"step": torch.tensor(float(b["step"])), "exp_avg": b["m"][o:o + n].view(p.shape).clone(),
+                                 "exp_avg_sq": b["v"][o:o + n].view(p.shape).clone()}
+        try:
+            return super().state_dict()
+        finally:
+            for b in self._buckets:
+                if b is not None:
+                    for p in b["params"]:
+                        self.state.pop(p, None)
+
+    def load_state_dict(self, state_dict) -> None:
+        super().load_state_dict(state_dict)          # fills self.state[param] with tensors on the parameter's device
+        with torch.no_grad():
+            for b in self._buckets:
+                if b is None:
+                    continue
+                for p, o in zip(b["params"], b["offs"]):
+                    st = self.state.pop(p, None)
+                    if st:
+                        n = p.numel()
+                        b["m"][o:o + n].copy_(st["exp_avg"].reshape(-1))
+                        b["v"][o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                        b["step"] = int(st["step"])
 
     # -- overlapped gradient reduction (dp.SegmentReducer does the bookkeeping) ----------------------
     def _world(self) -> int:
@@ -191,7 +236,8 @@ class FusedAdam(torch.optim.Optimizer):
             for p, o in zip(b["params"], b["offs"]):
                 if p.dim() >= 2:
                     p._avf_bf16 = (b["shadow"][o:o + p.numel()].view(p.shape), p._version)
-        AF.bump_weights_epoch()
+            for p in b["params"]:                               # per-parameter staleness: packed copies of OTHER (frozen) parameters stay valid
+                p._avf_wver = getattr(p, "_avf_wver", 0) + 1
         return loss
 
 

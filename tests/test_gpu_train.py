@@ -459,6 +459,68 @@ def test_graphed_hot_path_notices_weight_changes():
     check(False)
 
 
+def test_fused_adam_checkpoint_hooks_and_per_parameter_staleness():
+    """(1) FusedAdam.state_dict() / load_state_dict() carry exp_avg, exp_avg_sq and the step, so a resumed run continues the trajectory
+    bit for bit; (2) a parameter with a tensor hook gets its gradient through autograd (the hook fires) instead of the direct
+    accumulation into the bucket; (3) stepping some parameters does not invalidate the packed copies of frozen ones."""
+    T, B, seed = 8, 6, 73
+    stage3, frame, audio = O.synth_hot_path_inputs(seed, B, T)
+    labels = O.synth_inputs(seed, B, T, image=8)[2].cuda()
+    ins = (stage3.cuda().requires_grad_(True), frame.cuda().requires_grad_(True), audio.cuda().requires_grad_(True))
+
+    def hot(m):
+        return [q for k, q in m.named_parameters() if not O.is_backbone_key(k)]
+
+    def step(m, opt):
+        opt.zero_grad()
+        _, out21 = m.hot_path_train(*ins)
+        loss = m.get_au_loss(out21, labels)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    m1 = _model(seed, T, "bf16", dropout=0.0).train()
+    o1 = A.FusedAdam(hot(m1), lr=5e-4, weight_decay=5e-5)
+    for _ in range(3):
+        step(m1, o1)
+    sd_model = {k: v.clone() for k, v in m1.state_dict().items()}
+    sd_opt = o1.state_dict()
+    assert len(sd_opt["state"]) > 100 and all("exp_avg_sq" in v for v in sd_opt["state"].values())
+    ref = [step(m1, o1) for _ in range(2)]
+    # resume in a fresh model + optimiser (moments restored BEFORE the flat bucket exists)
+    m2 = _model(seed, T, "bf16", dropout=0.0).train()
+    m2.load_state_dict(sd_model, strict=True)
+    o2 = A.FusedAdam(hot(m2), lr=5e-4, weight_decay=5e-5)
+    o2.load_state_dict(sd_opt)
+    got = [step(m2, o2) for _ in range(2)]
+    assert got == ref, (got, ref)
+    n1, n2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    assert all(torch.equal(n1[k], n2[k]) for k in n1 if not O.is_backbone_key(k))
+    # ... and into an optimiser whose bucket already exists
+    o2.load_state_dict(o1.state_dict())
+    assert step(m2, o2) == step(m1, o1)
+
+    # (2) hooks
+    seen = []
+    w = m1.au_head.corr_transformer.layers[0][0].fn.fn.to_qkv.weight
+    h = w.register_hook(lambda g: seen.append(float(g.abs().sum())))
+    before = w.detach().clone()
+    step(m1, o1)
+    h.remove()
+    assert len(seen) == 1 and seen[0] > 0 and not torch.equal(before, w.detach())
+
+    # (3) frozen sub-model keeps its packed weights across optimiser steps of the others
+    m3 = _model(seed, T, "bf16", dropout=0.0).train()
+    for q in m3.video_model.video_model.t_former.parameters():
+        q.requires_grad_(False)
+    o3 = A.FusedAdam([q for q in hot(m3) if q.requires_grad], lr=5e-4)
+    step(m3, o3)
+    packed = m3.video_model.video_model.t_former.spatial_transformer.packed()
+    step(m3, o3)
+    assert m3.video_model.video_model.t_former.spatial_transformer.packed() is packed
+    assert m3.au_head.corr_transformer.packed() is not None
+
+
 def test_programmatic_dependent_launch_does_not_change_results():
     """Every kernel is launched with the programmatic-stream-serialization attribute and waits (griddepcontrol.wait) for its
     predecessor before touching memory: results must be bit-identical to plain launches (avf_set_pdl_enabled(0))."""
