@@ -42,6 +42,11 @@ using namespace fused;
 #ifndef AVF_PROD_FASTPATH
 #define AVF_PROD_FASTPATH 1
 #endif
+// 1: the normalised attention output O_h / l stays in TMEM (packed bf16 over its own accumulator columns) as the A operand of the
+// out-projection; 0: staged through shared memory (8 KB, needs a proxy fence per head)
+#ifndef AVF_O_TMEM
+#define AVF_O_TMEM 1
+#endif
 
 constexpr int DIM = 256, HEADS = 8, DH = 32;
 constexpr int MAX_DEPTH = 3, MAX_MLP = 1024;
@@ -503,10 +508,21 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_l) : "f"(sums[0] + sums[1]));
           }
 #endif
+          const uint64_t inv2 = f2_pack(inv_l, inv_l);
+#if AVF_O_TMEM
+          // O_h / l goes back INTO the accumulator's TMEM columns as packed bf16 (like P over S and gelu(H) over H): thread g turns its 16
+          // fp32 columns [16g, 16g + 16) into 8 packed columns at [16g, 16g + 8) — columns only it reads — and the out-projection takes
+          // its A operand from TMEM, one 16-wide k-step per thread.  No shared-memory staging, no generic->async proxy fence.
+          static_assert(OW == 16, "TMEM-resident O operand is written for two threads per row");
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = cvt_bf16x2_pair(f2_mul(f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), inv2));
+          tmem_st8(tl + TM_O + g * OW, pk);
+          tmem_st_wait();
+          w.arrive_tmem_only(B_O_DRAINED);
+#else
           uint8_t* ob = smem + OFF_OST + row * 64;
           const uint32_t sw = uint32_t((row >> 1) & 3);
-#pragma unroll
-          const uint64_t inv2 = f2_pack(inv_l, inv_l);
 #pragma unroll
           for (int c = 0; c < OW / 8; ++c) {
             uint4 pk;
@@ -517,6 +533,7 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
             *reinterpret_cast<uint4*>(ob + ((uint32_t(g * (OW / 8) + c) ^ sw) << 4)) = pk;
           }
           w.arrive(B_O_DRAINED);
+#endif
           pf.mark(PW_E3);
         }
         if (h < HEADS) {         // E2: softmax of this row over its own sequence's columns, P (bf16) over the S columns
@@ -902,9 +919,15 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   };
   auto outproj = [&](int h) {                 // x += (O_h / l) Wout[:, 32h .. 32h+32)^T   (x + b_out was stored by the workers)
     const uint32_t s = RING_LO + h % (RING_HI - RING_LO), sb = slot_wait(s);
-    const uint64_t da = desc_sw64(ost), db = desc_sw64(sb);
+    const uint64_t db = desc_sw64(sb);
+#if AVF_O_TMEM
+    if (leader) umma_bf16_ts(tmem + TM_X, tmem + TM_O, db, id_256, 1u);               // k-step 0: thread 0's packed columns
+    if (leader) umma_bf16_ts(tmem + TM_X, tmem + TM_O + 16, db + 2, id_256, 1u);      // k-step 1: thread 1's
+#else
+    const uint64_t da = desc_sw64(ost);
     if (leader) umma_bf16(tmem + TM_X, da, db, id_256, 1u);
     if (leader) umma_bf16(tmem + TM_X, da + 2, db + 2, id_256, 1u);
+#endif
     slot_release(s);
   };
   bool last_layer = false;
