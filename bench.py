@@ -266,7 +266,7 @@ def train_config(sample_note=None):
 def workload_config(sample_note=None):
     cfg = {"workload": f"avformer_hot_path_eval: {CLIPS_PER_GPU} clips/GPU x {N_FRAMES} frames "
                        f"(SFormer on {CLIPS_PER_GPU * N_FRAMES} stage-3 maps [256,7,7] + TFormer + AU_former x2 + fusion head -> 12-AU logits)",
-           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel; at N>1 every step ends with the NCCL all-gather of the [512, 21] logits of all ranks, in the stream, inside the timed region",
+           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel; at N>1 every step contains the NCCL all-gather of the [512, 21] logits of all ranks, inside the timed region (a branch of the captured graph behind the fusion head; complete when the step's graph ends)",
            "l2": "inputs (205 MB of stage-3 maps per step) are larger than the 126 MB L2; no explicit flush",
            "flop_per_clip": hot_path_flops_per_clip(N_FRAMES)}
     if sample_note:
@@ -356,13 +356,14 @@ def run_ours(args):
         sm_reserve = int(os.environ.get("AVF_SM_RESERVE", "0"))
         if sm_reserve > 0:
             L.avf_set_sm_cap(n_sm - sm_reserve)
-        graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split)
+        # the logit all-gather of N > 1.  ingraph (default): a branch of the captured graph that starts behind the fusion head and runs
+        # UNDER the SFormer kernel (dynamic tile scheduler); instream: an NCCL call behind every replay; pipelined: asynchronous, one batch late
+        gather_mode = os.environ.get("AVF_GATHER", "ingraph") if world > 1 else "none"      # developer A/B: ingraph | instream | pipelined | none
+        graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split,
+                                   gather_into=gathered if gather_mode == "ingraph" else None)
         L.avf_set_sm_cap(0)
 
         pipe = A.dp.PipelinedLogitGather()       # N > 1: the gather of batch i runs under the kernels of batch i+1
-        # in the stream, right behind the step's last kernel: measured on 8 B200s 1.309 ms per step against 1.317 ms for the asynchronous
-        # pipelined gather with two SMs reserved for NCCL (AVF_GATHER=pipelined AVF_SM_RESERVE=2) and 1.255 ms without any gather
-        gather_mode = os.environ.get("AVF_GATHER", "instream")      # developer A/B: instream | pipelined | none
 
         def gstep():
             _, out21, _ = graphed.replay()
@@ -382,6 +383,13 @@ def run_ours(args):
             e1.record()
             barrier()
         ms_total = e0.elapsed_time(e1)
+        gather_ok = None
+        if world > 1 and gather_mode in ("ingraph", "instream"):
+            # what the timed step gathered: my own shard sits at my rank's offset, and every rank holds the same [N * 512, 21] table
+            mine_ok = torch.equal(gathered[rank * B:(rank + 1) * B], graphed.out[1])
+            chk = torch.stack([gathered.double().sum(), -gathered.double().sum(), torch.tensor(0.0 if mine_ok else 1.0, dtype=torch.float64, device=dev)])
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+            gather_ok = bool(chk[0].item() == -chk[1].item() and chk[2].item() == 0.0)
         parity = timed_outputs_vs_oracle(model, graphed.out, host, T) if rank == 0 else None
 
         # ---- end to end from pinned host buffers ---------------------------------------------
@@ -468,7 +476,7 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "parity_max_err": parity["logits_max_abs_err"], "decisions_match": parity["decisions_match"], "parity": parity,
+            "gather": gather_mode, "gather_checked": gather_ok, "parity_max_err": parity["logits_max_abs_err"], "decisions_match": parity["decisions_match"], "parity": parity,
             "tensor_frac_whole_step": value / world * hot_path_flops_per_clip(T) / 1e12 / peaks["bf16_tflops_sustained"],
             "breakdown_ms": {"sformer": ms_sformer, "tformer": ms_tformer, "whole_step": ms_step, "whole_step_eager_launches": ms_eager},
             "flops_per_clip": {"algorithmic": hot_path_flops_per_clip(T), "executed": hot_path_flops_per_clip(T) - tformer_skipped_flops_per_clip(T),

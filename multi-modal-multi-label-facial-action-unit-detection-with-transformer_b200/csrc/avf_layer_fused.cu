@@ -105,9 +105,20 @@ constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, T
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
   B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_X2_FULL,
-  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, NUM_BARS = B_G_FULL + 8
+  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, B_TQ_FULL = B_G_FULL + 8, NUM_BARS = B_TQ_FULL + 4
 };
-static_assert(NUM_BARS * 8 + 8 <= 512, "barrier block");
+static_assert(NUM_BARS * 8 + 8 + 16 <= 512, "barrier block (+ TMEM slot + tile queue)");
+
+// Tile scheduler.  The first tile of a CTA is blockIdx.x; the following ones come from an atomic counter (DYNAMIC: the persistent grid
+// then balances itself — a CTA that starts late because an NCCL kernel or a neighbouring stream holds its SM, or that runs on a
+// slower-clocked part of the chip, simply takes fewer tiles instead of finishing a fixed share late) or from static striding.  The
+// weight producer fetches the index of tile k+1 while it issues tile k and publishes it through a four-entry queue in shared
+// memory (one mbarrier per entry); the other roles read entry k when they get there.  -1 ends the loop.
+__device__ __forceinline__ int* tile_queue(uint64_t* bars) { return reinterpret_cast<int*>(bars + NUM_BARS) + 2; }   // behind the TMEM slot word
+__device__ __forceinline__ int next_tile(uint64_t* bars, uint32_t k) {
+  mbar_wait(&bars[B_TQ_FULL + (k & 3u)], (k >> 2) & 1u);
+  return *reinterpret_cast<volatile int*>(tile_queue(bars) + (k & 3u));
+}
 
 enum { IO_NCHW_BF16 = 0, IO_ROWS_F32 = 1 };
 constexpr int POS_LD = 64;   // row stride of the channel-major positional table
@@ -136,6 +147,7 @@ struct FusedArgs {
   const float* pos_t;        // IO_NCHW_BF16: the same table as [256 / 4][POS_LD tokens][4 channels]: one 16-byte load per 4 channels,
                              // and the lanes of a warp (consecutive tokens) read consecutive 16-byte words
   int ld_in, ld_out;         // IO_ROWS_F32 row strides (elements)
+  int* tile_counter;         // dynamic tile scheduler: a zeroed device counter (nullptr = static striding, tile = blockIdx.x + k * gridDim.x)
   int n_seq, n_tok, slot, slot_log2, spt, n_tiles, n_chunks, depth;
 };
 
@@ -374,7 +386,9 @@ __device__ void worker_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, u
   Prof pf;
   pf.start(blockIdx.x == 0 && wt == 0);
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  for (uint32_t tk = 0;; ++tk) {
+    const int tile = next_tile(bars, tk);
+    if (tile < 0) break;
     const int seqs_here = min(spt, a.n_seq - tile * spt);
     const bool valid = seq_in_tile < seqs_here && t_in_seq < n_tok;
     const size_t grow = (size_t(tile) * spt + seq_in_tile) * n_tok + t_in_seq;     // global token row (IO_ROWS_F32)
@@ -740,11 +754,11 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
   uint32_t it = 0;
   // Input frames of the NEXT tile go into A0 as soon as the MMAs of the current tile are done with it (B_A0_FREE, one
   // completion per tile).  Polled between weight slots so that this thread never blocks on it.
-  int load_tile = blockIdx.x;
+  int load_tile = blockIdx.x;                   // tile whose input frames are to be loaded next (-1: none pending)
   uint32_t n_free = 0;
   bool need_free = false;
   auto poll_loader = [&]() {
-    if (IO != IO_NCHW_BF16 || load_tile >= a.n_tiles) return;
+    if (IO != IO_NCHW_BF16 || load_tile < 0) return;
     if (need_free) {
 #if AVF_PROD_POLL >= 1
       if (!mbar_test_wait(&bars[B_A0_FREE], n_free & 1)) return;     // a probe that never suspends: this thread has weight slots to serve
@@ -757,7 +771,7 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     const uint32_t bytes = uint32_t(seqs_here) * a.n_tok * DIM * 2;
     mbar_expect_tx(&bars[B_X0_FULL], bytes);
     bulk_load_1d(smem + OFF_A0, static_cast<const __nv_bfloat16*>(a.in) + size_t(load_tile) * a.spt * a.n_tok * DIM, bytes, &bars[B_X0_FULL]);
-    load_tile += gridDim.x;
+    load_tile = -1;
     need_free = true;
   };
   // Slot s is refilled once its previous content has been consumed (per-slot parity bits: the out-projection slices rotate over
@@ -802,7 +816,25 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
     tma_load_2d(smem + slot_offset(s), tm, full_bar, c0, c1);
     ++it;
   };
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  // tile scheduler (see next_tile): this thread owns the queue
+  uint32_t kpub = 0;
+  auto publish = [&](int t) {
+    tile_queue(bars)[kpub & 3u] = t;
+    mbar_arrive(&bars[B_TQ_FULL + (kpub & 3u)]);
+    ++kpub;
+  };
+  int cur = blockIdx.x;
+  publish(cur);
+  for (;;) {
+    int nxt;
+    if (a.tile_counter != nullptr) nxt = atomicAdd(a.tile_counter, 1) + int(gridDim.x);
+    else nxt = cur + int(gridDim.x);
+    if (nxt >= a.n_tiles) nxt = -1;
+    publish(nxt);
+    if (IO == IO_NCHW_BF16) {
+      while (load_tile >= 0) poll_loader();     // the frames of `cur` are on their way (normally long since) before `nxt` becomes the pending load
+      load_tile = nxt;
+    }
     for (int l = 0; l < a.depth; ++l) {
       const LayerArgs& L = a.layer[l];
       for (int h = 0; h < HEADS; ++h) {                        // Wout[:, 32h .. 32h+32): [256 x 32], 64B swizzle
@@ -831,6 +863,8 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
         if (c + 2 < a.n_chunks) ff1(c + 2);
       }
     }
+    if (nxt < 0) break;
+    cur = nxt;
   }
 }
 
@@ -841,7 +875,7 @@ template <int IO>
 __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars) {
   uint32_t qit = 0, hq = 0, n_free = 0, n_read = 0;
   bool first = true;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  for (uint32_t tk = 0; next_tile(bars, tk) >= 0; ++tk) {
     // A1 doubles as the NCHW output staging: the previous tile's bulk store must have read it (signalled after this tile's input sweep)
     if constexpr (IO == IO_NCHW_BF16) mbar_wait(&bars[B_OUT_READ], (n_read++) & 1);
     for (int l = 0; l < a.depth; ++l) {
@@ -945,7 +979,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     if (c == a.n_chunks - 1 && last_layer) if (leader) umma_commit(&bars[B_A0_FREE]);
   };
 
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  for (uint32_t tk = 0; next_tile(bars, tk) >= 0; ++tk) {
     for (int l = 0; l < a.depth; ++l) {
       last_layer = l == a.depth - 1;
       mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
@@ -1084,11 +1118,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
 }
 
 // pos [n_tok, 256] -> pos_t [256 / 4][POS_LD][4] (one tiny launch in front of the fused kernel; 64 KB)
-__global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restrict__ pos, float* __restrict__ pos_t, int n_tok) {
+__global__ void __launch_bounds__(256) pos_transpose_kernel(const float* __restrict__ pos, float* __restrict__ pos_t, int n_tok, int* tile_counter) {
   pdl_wait();      // programmatic dependent launch: everything above is launch overhead hidden behind the previous kernel
   pdl_trigger();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && tile_counter != nullptr) *tile_counter = 0;      // the fused kernel's tile scheduler starts from zero
   const int c = blockIdx.x * 4 + (threadIdx.x & 3), t = threadIdx.x >> 2;
   pos_t[(blockIdx.x * POS_LD + t) * 4 + (threadIdx.x & 3)] = t < n_tok ? pos[t * DIM + c] : 0.f;
+}
+
+bool dynamic_tiles_enabled() {    // developer A/B: AVF_FUSED_DYNAMIC_TILES=0 keeps static striding for the NCHW form too
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AVF_FUSED_DYNAMIC_TILES");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 bool fixed_ntok_enabled() {      // developer A/B: AVF_FUSED_FIXED_NTOK=0 keeps the run-time-geometry instantiation for the SFormer too
@@ -1131,7 +1175,7 @@ bool encoder_fused_supported(const avf_stack_shape* s) {
 }
 
 // io_kind 0: in/out are NCHW bf16 maps [n_seq, 256, n_tok] (pos required); 1: fp32 token rows with strides ld_in / ld_out.
-size_t encoder_fused_scratch_bytes() { return size_t(DIM) * POS_LD * sizeof(float); }
+size_t encoder_fused_scratch_bytes() { return size_t(DIM) * POS_LD * sizeof(float) + 64; }      // positional table + the tile scheduler's counter
 
 int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights* L, const void* in, int ld_in, void* out, int ld_out,
                   const float* pos, void* scratch, cudaStream_t st) {
@@ -1143,8 +1187,10 @@ int encoder_fused(int io_kind, const avf_stack_shape* s, const avf_layer_weights
   static thread_local FusedArgs a;      // ~2 KB of tensor maps + pointers, passed by value (__grid_constant__) per launch
   static_assert(sizeof(FusedArgs) <= 4000, "kernel parameter space");
   a.in = in; a.out = out; a.pos = pos; a.pos_t = static_cast<const float*>(scratch); a.ld_in = ld_in; a.ld_out = ld_out;
+  a.tile_counter = nullptr;
   if (io_kind == IO_NCHW_BF16) {
-    launch_pdl(pos_transpose_kernel, DIM / 4, 256, 0, st, pos, static_cast<float*>(scratch), s->n_tok);
+    if (dynamic_tiles_enabled()) a.tile_counter = reinterpret_cast<int*>(static_cast<uint8_t*>(scratch) + size_t(DIM) * POS_LD * sizeof(float));
+    launch_pdl(pos_transpose_kernel, DIM / 4, 256, 0, st, pos, static_cast<float*>(scratch), s->n_tok, a.tile_counter);
     AVF_LAUNCH_CHECK("pos_transpose_kernel");
   }
   a.n_seq = s->n_seq; a.n_tok = s->n_tok;

@@ -58,8 +58,11 @@ class GraphedHotPath:
     """model.hot_path(...) captured for fixed input shapes.  Inputs are copied into static buffers (device-to-device or
     host-to-device), outputs are the graph's static tensors (valid until the next replay)."""
 
-    def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor, sm_split=None):
-        """sm_split = (sformer_sms, chain_sms[, frames_beside]): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the
+    def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor, sm_split=None, gather_into: Optional[torch.Tensor] = None):
+        """gather_into = a [world * n_clips, 21] fp32 tensor: the evaluation-time all-gather of the logits is
+        captured INSIDE the graph as a branch that starts the moment the fusion head has written the logits and joins at the end, so it
+        runs under the SFormer kernel that follows (whose dynamic tile scheduler absorbs the few SMs NCCL's CTAs hold for a while).
+        sm_split = (sformer_sms, chain_sms[, frames_beside]): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the
         TFormer / AU_former / fusion-head chain, whose persistent GEMMs are capped at `chain_sms` CTAs (every persistent CTA of
         either family owns a whole SM, so the two grids partition the GPU).  With `frames_beside` only that many leading
         stage-3 maps go through the side-by-side launch — sized to last about as long as the chain, half of whose kernels
@@ -70,6 +73,11 @@ class GraphedHotPath:
         if sm_split is None and os.environ.get("AVF_SM_SPLIT", "") not in ("", "0", "off"):
             sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
         self.sm_split = tuple(sm_split) if sm_split else None
+        self.gather_into = gather_into
+        if gather_into is not None:
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("GraphedHotPath(gather_into=...) needs an initialised torch.distributed process group")
         self.side2 = torch.cuda.Stream()
         self.model = model
         self.stage3, self.frame = stage3.clone(), frame.clone()
@@ -112,6 +120,10 @@ class GraphedHotPath:
         m.video_model.au_head.tokens_into(cls, cls.shape[1], n_clips, out=fused[:, 128:], ld_out=256)
         cur.wait_stream(self.side)
         out21, dec = m.au_head.logits21_(fused, n_clips, True)
+        work = None
+        if self.gather_into is not None:
+            import torch.distributed as dist
+            work = dist.all_gather_into_tensor(self.gather_into, out21, async_op=True)      # a graph branch from here ...
         if self.sm_split is not None:
             L.avf_set_sm_cap(old_cap)
             cur.wait_stream(self.side2)
@@ -119,6 +131,8 @@ class GraphedHotPath:
                 vm.s_former.sformer(self.stage3[n_beside:], out=s_out[n_beside:])
         else:
             s_out = vm.s_former.sformer(self.stage3)
+        if work is not None:
+            work.wait()                                                                      # ... joined here, behind the SFormer
         return s_out, out21, dec
 
     def replay(self, stage3: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None, audio: Optional[torch.Tensor] = None):
