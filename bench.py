@@ -486,8 +486,11 @@ def run_ours(args):
                            + (f"; SFormer kernel on {sm_split[0]} SMs next to the TFormer/head chain on {sm_split[1]} SMs (avf_set_sm_cap)" if sm_split else ""),
             "train": {"see": "python bench.py --mode train (its own JSON line, reference arm and end-to-end number)"},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        graphed.release()                        # the graph holds NCCL nodes (in-graph gather): it goes before the communicator
+        del graphed
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -135,7 +135,17 @@ class GraphedHotPath:
             work.wait()                                                                      # ... joined here, behind the SFormer
         return s_out, out21, dec
 
+    def release(self) -> None:
+        """Destroy the captured graph.  With gather_into the graph holds NCCL kernel nodes, and the communicator cannot be torn down
+        (dist.destroy_process_group() blocks) while such a graph is alive: call this first."""
+        torch.cuda.synchronize()
+        self.graph.reset()
+        self.graph = None
+        self.out = None
+
     def replay(self, stage3: Optional[torch.Tensor] = None, frame: Optional[torch.Tensor] = None, audio: Optional[torch.Tensor] = None):
+        if self.graph is None:
+            raise RuntimeError("GraphedHotPath.replay() after release()")
         if stage3 is not None and stage3.data_ptr() != self.stage3.data_ptr():
             self.stage3.copy_(stage3, non_blocking=True)
         if frame is not None and frame.data_ptr() != self.frame.data_ptr():

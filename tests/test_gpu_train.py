@@ -410,6 +410,42 @@ def test_graphed_hot_path_equals_eager(sm_split):
             assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
 
 
+def test_graphed_hot_path_with_the_logit_gather_inside_the_graph():
+    """GraphedHotPath(gather_into=...): the NCCL all-gather is a branch of the captured graph (here: a one-rank communicator on this
+    GPU).  The gathered table holds this rank's logits after every replay, nothing else changes, and release() lets the process
+    group go away afterwards."""
+    import socket
+    import torch.distributed as dist
+    if dist.is_initialized():
+        pytest.skip("a process group is already up in this process")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        T, B, seed = 16, 6, 71
+        m = _model(seed, T, "bf16", dropout=0.0).eval()
+        s3, fr, au = O.synth_hot_path_inputs(seed, B, T)
+        dev = (s3.bfloat16().cuda(), fr.bfloat16().cuda(), au.cuda())
+        gathered = torch.full((B, 21), float("nan"), device="cuda")
+        with torch.no_grad():
+            g = A.GraphedHotPath(m, *dev, gather_into=gathered)
+            for it in range(3):
+                s3, fr, au = O.synth_hot_path_inputs(seed + it, B, T)
+                dev = (s3.bfloat16().cuda(), fr.bfloat16().cuda(), au.cuda())
+                s_ref, o_ref, d_ref = m.hot_path(*dev, want_decisions=True)
+                gathered.fill_(float("nan"))
+                s_out, o, d = g.replay(*dev)
+                torch.cuda.synchronize()
+                assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
+                assert torch.equal(gathered, o_ref)
+        g.release()
+        with pytest.raises(RuntimeError, match="release"):
+            g.replay()
+    finally:
+        dist.destroy_process_group()
+
+
 def test_graphed_hot_path_notices_weight_changes():
     """A captured graph points at the packed (bf16 / stacked) copies of the weights.  After optimizer.step(), load_state_dict() or an
     in-place edit the eager path re-packs and frees them; the graph has to notice and capture again instead of replaying with stale
