@@ -266,7 +266,7 @@ def train_config(sample_note=None):
 def workload_config(sample_note=None):
     cfg = {"workload": f"avformer_hot_path_eval: {CLIPS_PER_GPU} clips/GPU x {N_FRAMES} frames "
                        f"(SFormer on {CLIPS_PER_GPU * N_FRAMES} stage-3 maps [256,7,7] + TFormer + AU_former x2 + fusion head -> 12-AU logits)",
-           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel; at N>1 every step contains the NCCL all-gather of the [512, 21] logits of all ranks, inside the timed region (a branch of the captured graph behind the fusion head; complete when the step's graph ends)",
+           "clips_per_gpu": CLIPS_PER_GPU, "n_frames": N_FRAMES, "parallelism": "clip-sharded data parallel; at N>1 every step contains the NCCL all-gather of the [512, 21] logits of all ranks, inside the timed region (pushed over NVLink peer memory from inside the captured graph right behind the fusion head; the step's graph ends with the wait for all N blocks)",
            "l2": "inputs (205 MB of stage-3 maps per step) are larger than the 126 MB L2; no explicit flush",
            "flop_per_clip": hot_path_flops_per_clip(N_FRAMES)}
     if sample_note:
@@ -356,11 +356,23 @@ def run_ours(args):
         sm_reserve = int(os.environ.get("AVF_SM_RESERVE", "0"))
         if sm_reserve > 0:
             L.avf_set_sm_cap(n_sm - sm_reserve)
-        # the logit all-gather of N > 1.  ingraph (default): a branch of the captured graph that starts behind the fusion head and runs
-        # UNDER the SFormer kernel (dynamic tile scheduler); instream: an NCCL call behind every replay; pipelined: asynchronous, one batch late
-        gather_mode = os.environ.get("AVF_GATHER", "ingraph") if world > 1 else "none"      # developer A/B: ingraph | instream | pipelined | none
+        # the logit gather of N > 1.  peer (default): pushes over NVLink peer memory inside the captured graph (csrc/avf_peer.cu: push behind
+        # the fusion head, bounded wait at the end of the step); instream: an NCCL all-gather behind every replay (1.183 ms per step on 8 B200s
+        # against 1.107 ms on one); ingraph: the NCCL all-gather as a graph branch under the SFormer kernel (1.303 ms: slower, the two grids
+        # race for SMs); pipelined: NCCL, asynchronous, one batch late
+        gather_mode = os.environ.get("AVF_GATHER", "peer") if world > 1 else "none"      # developer A/B: peer | ingraph | instream | pipelined | none
+        peer, gather_note = None, None
+        if gather_mode == "peer":
+            try:
+                peer = A.dp.PeerLogitGather(B, 21)
+            except Exception as ex:                 # no peer mapping on this box (symmetric memory unavailable): NCCL in the stream instead, and say so
+                gather_note = f"peer-memory gather unavailable ({type(ex).__name__}: {str(ex)[:160]}); NCCL all-gather in the stream instead"
+            agree = torch.tensor([1 if peer is not None else 0], device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0:
+                peer, gather_mode = None, "instream"
         graphed = A.GraphedHotPath(model, devin["stage3"], devin["frame"], devin["audio"], sm_split=sm_split,
-                                   gather_into=gathered if gather_mode == "ingraph" else None)
+                                   gather_into=peer if peer is not None else (gathered if gather_mode == "ingraph" else None))
         L.avf_set_sm_cap(0)
 
         pipe = A.dp.PipelinedLogitGather()       # N > 1: the gather of batch i runs under the kernels of batch i+1
@@ -384,10 +396,13 @@ def run_ours(args):
             barrier()
         ms_total = e0.elapsed_time(e1)
         gather_ok = None
-        if world > 1 and gather_mode in ("ingraph", "instream"):
+        if world > 1 and gather_mode in ("peer", "ingraph", "instream"):
             # what the timed step gathered: my own shard sits at my rank's offset, and every rank holds the same [N * 512, 21] table
-            mine_ok = torch.equal(gathered[rank * B:(rank + 1) * B], graphed.out[1])
-            chk = torch.stack([gathered.double().sum(), -gathered.double().sum(), torch.tensor(0.0 if mine_ok else 1.0, dtype=torch.float64, device=dev)])
+            if peer is not None:
+                peer.check()                     # no wait timed out, device and host step counts agree
+            tbl = peer.table() if peer is not None else gathered
+            mine_ok = torch.equal(tbl[rank * B:(rank + 1) * B], graphed.out[1])
+            chk = torch.stack([tbl.double().sum(), -tbl.double().sum(), torch.tensor(0.0 if mine_ok else 1.0, dtype=torch.float64, device=dev)])
             dist.all_reduce(chk, op=dist.ReduceOp.MAX)
             gather_ok = bool(chk[0].item() == -chk[1].item() and chk[2].item() == 0.0)
         parity = timed_outputs_vs_oracle(model, graphed.out, host, T) if rank == 0 else None
@@ -476,7 +491,7 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "gather": gather_mode, "gather_checked": gather_ok, "parity_max_err": parity["logits_max_abs_err"], "decisions_match": parity["decisions_match"], "parity": parity,
+            "gather": gather_mode, "gather_note": gather_note, "gather_checked": gather_ok, "parity_max_err": parity["logits_max_abs_err"], "decisions_match": parity["decisions_match"], "parity": parity,
             "tensor_frac_whole_step": value / world * hot_path_flops_per_clip(T) / 1e12 / peaks["bf16_tflops_sustained"],
             "breakdown_ms": {"sformer": ms_sformer, "tformer": ms_tformer, "whole_step": ms_step, "whole_step_eager_launches": ms_eager},
             "flops_per_clip": {"algorithmic": hot_path_flops_per_clip(T), "executed": hot_path_flops_per_clip(T) - tformer_skipped_flops_per_clip(T),
@@ -488,8 +503,9 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        graphed.release()                        # the graph holds NCCL nodes (in-graph gather): it goes before the communicator
+        graphed.release()                        # a graph holding NCCL nodes (AVF_GATHER=ingraph) goes before the communicator
         del graphed
+        peer = None
         dist.barrier()
         dist.destroy_process_group()
 

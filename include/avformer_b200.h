@@ -197,6 +197,20 @@ int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels,
 int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
                             uint64_t* counts48, int32_t n_rows, void* stream);
 
+/* ---- evaluation-time logit gather over NVLink peer memory (replaces the host-side concatenation of the
+ * per-batch predictions in train.py:150-170 and the NCCL all-gather of a data-parallel evaluation) ------------------------------
+ * Every rank owns one PEER-MAPPED block of avf_peer_gather_bytes(world, n_floats) bytes, zeroed once, laid out as
+ * table[2][world][n_floats] fp32 followed (128-byte aligned) by flags[2][world] u32.  peer_base = DEVICE array of the `world` base
+ * pointers as mapped into this process (own block included).  state = two DEVICE words, zeroed once: [0] step counter, [1] error.
+ * avf_logits_push: store my n_floats logits into slot (step & 1), row block `rank`, of every peer's table and release the flag.
+ * avf_logits_wait: spin (bounded by timeout_ns; on expiry state[1] = 1 + the missing rank) until all `world` blocks of the step
+ * are in MY table, then step += 1.  The complete table of step i is table[i & 1]; it is overwritten by the pushes of step i + 2,
+ * which no rank issues before every rank has pushed step i + 1 — so read it before this rank's push of step i + 1 (stream order).
+ * Both are asynchronous on `stream`, graph-capturable, and must be issued the same number of times on every rank. */
+size_t avf_peer_gather_bytes(int32_t world, size_t n_floats);
+int avf_logits_push(const float* logits, size_t n_floats, const uint64_t* peer_base, int32_t world, int32_t rank, const uint32_t* state, void* stream);
+int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_t* state, uint64_t timeout_ns, void* stream);
+
 /* ---- parameter preparation ------------------------------------------------------------------ */
 int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

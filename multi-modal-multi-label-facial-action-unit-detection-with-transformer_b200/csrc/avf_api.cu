@@ -366,6 +366,24 @@ int avf_au_bce_loss(const float* logits, int32_t ld_logits, const float* labels,
   return au_bce(logits, ld_logits, labels, pos_weight, loss_out, dlogits, n_clips, static_cast<cudaStream_t>(stream));
 }
 
+size_t avf_peer_gather_bytes(int32_t world, size_t n_floats) { return (world > 0 && world <= 1024) ? peer_gather_bytes(world, n_floats) : 0; }
+
+int avf_logits_push(const float* logits, size_t n_floats, const uint64_t* peer_base, int32_t world, int32_t rank, const uint32_t* state, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(logits && peer_base && state, AVF_EINVAL, "logits_push: null pointer");
+  AVF_REQUIRE(world > 0 && world <= 1024 && rank >= 0 && rank < world && n_floats > 0, AVF_EINVAL, "logits_push: world %d rank %d n %zu", world, rank, n_floats);
+  return logits_push(logits, n_floats, reinterpret_cast<const unsigned long long*>(peer_base), world, rank, state, static_cast<cudaStream_t>(stream));
+}
+
+int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_t* state, uint64_t timeout_ns, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(my_base && state, AVF_EINVAL, "logits_wait: null pointer");
+  AVF_REQUIRE(world > 0 && world <= 1024 && n_floats > 0, AVF_EINVAL, "logits_wait: world %d n %zu", world, n_floats);
+  return logits_wait(my_base, n_floats, world, state, timeout_ns, static_cast<cudaStream_t>(stream));
+}
+
 int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
                             uint64_t* counts48, int32_t n_rows, void* stream) {
   int e = require_device();

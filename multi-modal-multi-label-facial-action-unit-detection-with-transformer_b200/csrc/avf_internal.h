@@ -21,6 +21,10 @@ int cast_f32_bf16(const float* s, void* d, size_t n, cudaStream_t st);
 int cast_bf16_f32(const void* s, float* d, size_t n, cudaStream_t st);
 int au_logits(const float* x, int ld_x, const float* w_last, float* out21, int* decisions, int n_clips, int dim, cudaStream_t st);
 int au_bce(const float* logits, int ld, const float* labels, const float* pw, float* loss_out, float* dlogits, int n_clips, cudaStream_t st);
+// avf_peer.cu: logit gather as pushes over NVLink peer memory
+size_t peer_gather_bytes(int world, size_t n);
+int logits_push(const float* logits, size_t n, const unsigned long long* peer_base, int world, int rank, const uint32_t* state, cudaStream_t st);
+int logits_wait(const void* my_base, size_t n, int world, uint32_t* state, unsigned long long timeout_ns, cudaStream_t st);
 int au_confusion(const float* pred, int ld_pred, float thresh, const float* labels, int ld_lab, float ignore, unsigned long long* counts, int n_rows,
                  cudaStream_t st);
 

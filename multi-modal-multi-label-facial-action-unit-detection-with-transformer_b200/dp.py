@@ -86,6 +86,79 @@ class PipelinedLogitGather:
                 self.work[i] = None
 
 
+class PeerLogitGather:
+    """The evaluation-time logit gather as PUSHES over NVLink peer memory (csrc/avf_peer.cu, include/avformer_b200.h
+    avf_logits_push / avf_logits_wait) instead of a collective: ``push(out21)`` stores the rank's [b, 21] logits straight into every
+    peer's table and returns at once; ``wait()`` — issued at the end of the step, behind whatever independent work follows the
+    fusion head — blocks the STREAM (not the host) until the blocks of all ranks for that step have arrived, which they usually
+    have long before.  No per-step rendezvous: a rank may run ahead of the slowest peer by most of a step.
+
+    The peer-mapped block comes from torch symmetric memory (torch.distributed._symmetric_memory: allocation + exchange of the
+    handles inside one node); the kernels are ours.  Every rank must issue the same sequence of push / wait pairs.  Both calls are
+    graph-capturable: the step counter lives on the device; ``table()`` follows it on the host (``note_replay()`` after each replay
+    of a graph that contains a captured pair)."""
+
+    def __init__(self, rows_per_rank: int, cols: int = 21, group=None, timeout_s: float = 5.0):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerLogitGather needs an initialised torch.distributed process group (NCCL, one node)")
+        self._ct = ctypes
+        self._L = _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.rows, self.cols, self.n = int(rows_per_rank), int(cols), int(rows_per_rank) * int(cols)
+        self.timeout_ns = int(timeout_s * 1e9)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        nbytes = int(_lib.lib().avf_peer_gather_bytes(self.world, self.n))
+        self.block = symm.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        self.block.zero_()
+        self.handle = symm.rendezvous(self.block, self.group)
+        ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.block.data_ptr():
+            raise RuntimeError("PeerLogitGather: symmetric-memory rendezvous returned an unexpected pointer table")
+        self.peer_base = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int32, device=dev)          # [0] step counter, [1] error word
+        self.done = 0                                                        # host mirror of the step counter
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                                             # every table is zeroed before anybody pushes
+
+    def push(self, out21: torch.Tensor) -> None:
+        if not (out21.is_cuda and out21.dtype == torch.float32 and out21.is_contiguous() and out21.numel() == self.n):
+            raise ValueError(f"PeerLogitGather.push: expected a contiguous fp32 CUDA tensor of {self.rows} x {self.cols}, got {tuple(out21.shape)} {out21.dtype}")
+        c = self._ct.c_void_p
+        self._L.check(self._L.lib().avf_logits_push(c(out21.data_ptr()), self.n, c(self.peer_base.data_ptr()), self.world, self.rank,
+                                                    c(self.state.data_ptr()), c(torch.cuda.current_stream().cuda_stream)), "avf_logits_push")
+
+    def wait(self) -> None:
+        c = self._ct.c_void_p
+        self._L.check(self._L.lib().avf_logits_wait(c(self.block.data_ptr()), self.n, self.world, c(self.state.data_ptr()), self.timeout_ns,
+                                                    c(torch.cuda.current_stream().cuda_stream)), "avf_logits_wait")
+        if not torch.cuda.is_current_stream_capturing():
+            self.done += 1
+
+    def note_replay(self, pairs: int = 1) -> None:
+        """A captured graph holding `pairs` push / wait pairs has been replayed."""
+        self.done += pairs
+
+    def table(self) -> torch.Tensor:
+        """[world * rows, cols] logits of the last completed step (stream-ordered behind its wait; overwritten two steps later)."""
+        if self.done == 0:
+            raise RuntimeError("PeerLogitGather.table() before the first push / wait pair")
+        slot = (self.done - 1) & 1
+        return self.block[slot * self.world * self.n:(slot + 1) * self.world * self.n].view(self.world * self.rows, self.cols)
+
+    def check(self) -> None:
+        """Synchronise and raise if a wait ever timed out (a rank that stopped pushing) or the host mirror lost count."""
+        torch.cuda.synchronize()
+        step, err = (int(v) for v in self.state.tolist())
+        if err != 0:
+            raise RuntimeError(f"PeerLogitGather: the block of rank {err - 1} did not arrive within {self.timeout_ns / 1e9:.1f} s")
+        if step != self.done:
+            raise RuntimeError(f"PeerLogitGather: device step counter {step} != host count {self.done} (missing note_replay()?)")
+
+
 class SegmentReducer:
     """Gradient all-reduce overlapped with the backward pass.  The flat gradient bucket is laid out in contiguous segments, one
     per stack, in the order the stacks finish their backward (optim.FusedAdam).  ``ready(params)`` is called whenever the kernels

@@ -59,9 +59,11 @@ class GraphedHotPath:
     host-to-device), outputs are the graph's static tensors (valid until the next replay)."""
 
     def __init__(self, model, stage3: torch.Tensor, frame: torch.Tensor, audio: torch.Tensor, sm_split=None, gather_into: Optional[torch.Tensor] = None):
-        """gather_into = a [world * n_clips, 21] fp32 tensor: the evaluation-time all-gather of the logits is
-        captured INSIDE the graph as a branch that starts the moment the fusion head has written the logits and joins at the end, so it
-        runs under the SFormer kernel that follows (whose dynamic tile scheduler absorbs the few SMs NCCL's CTAs hold for a while).
+        """gather_into: the evaluation-time gather of the logits INSIDE the captured graph.
+        A dp.PeerLogitGather: its push kernel (NVLink peer stores, no rendezvous) sits right behind the fusion head and its wait at
+        the very end, behind the SFormer kernel — the default of bench.py at N > 1.  A [world * n_clips, 21] fp32 tensor: an NCCL
+        all-gather as a graph branch from the fusion head to the end (measured SLOWER than the in-stream call on 8 GPUs: NCCL's CTAs
+        and the persistent SFormer grid race for SMs and a rank whose gather started late stalls the others'; kept for A/B).
         sm_split = (sformer_sms, chain_sms[, frames_beside]): run the persistent SFormer kernel on `sformer_sms` SMs NEXT TO the
         TFormer / AU_former / fusion-head chain, whose persistent GEMMs are capped at `chain_sms` CTAs (every persistent CTA of
         either family owns a whole SM, so the two grids partition the GPU).  With `frames_beside` only that many leading
@@ -74,6 +76,7 @@ class GraphedHotPath:
             sm_split = tuple(int(v) for v in os.environ["AVF_SM_SPLIT"].split(","))
         self.sm_split = tuple(sm_split) if sm_split else None
         self.gather_into = gather_into
+        self._peer = gather_into if hasattr(gather_into, "push") else None
         if gather_into is not None:
             import torch.distributed as dist
             if not (dist.is_available() and dist.is_initialized()):
@@ -121,7 +124,9 @@ class GraphedHotPath:
         cur.wait_stream(self.side)
         out21, dec = m.au_head.logits21_(fused, n_clips, True)
         work = None
-        if self.gather_into is not None:
+        if self._peer is not None:
+            self._peer.push(out21)
+        elif self.gather_into is not None:
             import torch.distributed as dist
             work = dist.all_gather_into_tensor(self.gather_into, out21, async_op=True)      # a graph branch from here ...
         if self.sm_split is not None:
@@ -131,6 +136,8 @@ class GraphedHotPath:
                 vm.s_former.sformer(self.stage3[n_beside:], out=s_out[n_beside:])
         else:
             s_out = vm.s_former.sformer(self.stage3)
+        if self._peer is not None:
+            self._peer.wait()
         if work is not None:
             work.wait()                                                                      # ... joined here, behind the SFormer
         return s_out, out21, dec
@@ -158,6 +165,8 @@ class GraphedHotPath:
             self.recaptures += 1
             self._capture()
         self.graph.replay()
+        if self._peer is not None:
+            self._peer.note_replay()
         return self.out
 
 

@@ -442,6 +442,33 @@ def test_graphed_hot_path_with_the_logit_gather_inside_the_graph():
         g.release()
         with pytest.raises(RuntimeError, match="release"):
             g.replay()
+
+        # the same with the gather as pushes over peer memory (csrc/avf_peer.cu); one rank: its own block is the only peer
+        peer = A.dp.PeerLogitGather(B, 21, timeout_s=2.0)
+        o_eager = torch.randn(B, 21, device="cuda")
+        peer.push(o_eager)
+        peer.wait()
+        assert torch.equal(peer.table(), o_eager)
+        with torch.no_grad():
+            g = A.GraphedHotPath(m, *dev, gather_into=peer)
+            tables = []
+            for it in range(4):
+                s3, fr, au = O.synth_hot_path_inputs(seed + 10 + it, B, T)
+                dev = (s3.bfloat16().cuda(), fr.bfloat16().cuda(), au.cuda())
+                s_ref, o_ref, d_ref = m.hot_path(*dev, want_decisions=True)
+                s_out, o, d = g.replay(*dev)
+                torch.cuda.synchronize()
+                assert torch.equal(s_out, s_ref) and torch.equal(o, o_ref) and torch.equal(d, d_ref)
+                assert torch.equal(peer.table(), o_ref)
+                tables.append(peer.table())
+            assert tables[-1].data_ptr() != tables[-2].data_ptr() and tables[-1].data_ptr() == tables[-3].data_ptr()      # two slots, alternating
+        peer.check()
+        g.release()
+        # a block that never arrives: the wait gives up after its timeout and reports the missing rank instead of hanging the GPU
+        lone = A.dp.PeerLogitGather(B, 21, timeout_s=0.05)
+        lone.wait()
+        with pytest.raises(RuntimeError, match="rank 0 did not arrive"):
+            lone.check()
     finally:
         dist.destroy_process_group()
 
