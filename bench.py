@@ -648,7 +648,10 @@ def run_train(model, A, dev, rank, world, args):
                                "FLOPs (3 x forward) over the step time",
                      "peak_source": f"{peaks['source']} (sustained: a kernel chain timed inside a long step)", "algorithmic_flop_per_launch": flops_step},
         "cpu_baseline": cpu_baseline,
-        "grad_bucket_bytes": bucket_bytes, "grad_allreduce": ("per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer)" if opt.overlap else "one all-reduce of the flat bucket after backward") if world > 1 else None,
+        "grad_bucket_bytes": bucket_bytes, "grad_allreduce": ("per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer, NCCL)" if opt.overlap else
+                                                               ("one kernel over NVLink peer memory behind the backward (avf_grad_allreduce: two-shot, in place, deterministic)" if opt._buckets[0].get("peer") is not None
+                                                                else "one NCCL all-reduce of the flat bucket behind the backward")) if world > 1 else None,
+        "grad_allreduce_note": opt.reduce_note,
         "final_loss": final_loss,
         "launch_mode": "zero_grad + forward + AULoss + backward (+ the segment all-reduces at N>1) as ONE CUDA-graph replay, then the fused Adam launch",
     }
@@ -711,9 +714,25 @@ def run_dp_check(model, A, dev, rank, world):
     avg = bucket["g"].clone() / world
     if red is not None:
         red.disarm()
+    opt.overlap = False
+    opt._reducer = None
+    peer = bucket.get("peer")
+    if peer is not None:
+        # the same gradients through the one-kernel all-reduce over NVLink peer memory (FusedAdam's default): against the NCCL
+        # result above (another summation order: a few ulp), and the same bits on every rank
+        grads(*mine, reduce=False)
+        peer.reduce_()
+        res["grad_peer_reductions_completed"] = peer.check()
+        avg_peer = bucket["g"].clone() / world
+        res["grad_peer_vs_nccl_max_rel"] = ((avg_peer - avg).abs().max() / avg.abs().max()).item()
+        hi, lo = avg_peer.clone(), avg_peer.clone()
+        if world > 1:
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        res["grad_peer_identical_on_all_ranks"] = bool(torch.equal(hi, lo))
+    else:
+        res["grad_peer_note"] = opt.reduce_note
     if rank == 0:
-        opt.overlap = False
-        opt._reducer = None
         grads(*allin, reduce=False)                  # the same loss over the concatenated batch on ONE GPU (equal shard sizes: mean of means)
         big = bucket["g"]
         worst = 0.0
@@ -725,7 +744,8 @@ def run_dp_check(model, A, dev, rank, world):
                 worst = max(worst, (avg[o:o + n] - ref).abs().max().item() / scale)
         res["grad_max_rel_err"] = worst
         res["grad_segments_reduced_in_order"] = launched
-        res["ok"] = bool(res["logits_max_abs_diff"] <= 1e-5 and worst < 2e-3)
+        res["ok"] = bool(res["logits_max_abs_diff"] <= 1e-5 and worst < 2e-3
+                         and (peer is None or (res["grad_peer_vs_nccl_max_rel"] < 1e-5 and res["grad_peer_identical_on_all_ranks"])))
         print(json.dumps(res))
     ok = torch.tensor([1 if (rank != 0 or res.get("ok")) else 0], device=dev)
     if world > 1:

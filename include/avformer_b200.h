@@ -211,6 +211,17 @@ size_t avf_peer_gather_bytes(int32_t world, size_t n_floats);
 int avf_logits_push(const float* logits, size_t n_floats, const uint64_t* peer_base, int32_t world, int32_t rank, const uint32_t* state, void* stream);
 int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_t* state, uint64_t timeout_ns, void* stream);
 
+/* ---- data-parallel gradient all-reduce over NVLink peer memory (the reference trains on one GPU, train.py:206-236; this is the
+ * exchange step of the clip-sharded training of SURVEY.md section 8(e), in place of torch DDP / an NCCL all-reduce) -----------------
+ * Every rank keeps its flat fp32 gradient bucket of n_floats at the start of a PEER-MAPPED block of avf_peer_allreduce_bytes(world,
+ * n_floats) bytes (zeroed once: padding and two flag rows follow the bucket).  peer_base = DEVICE array of the `world` base pointers
+ * as mapped here; state = three DEVICE words zeroed once ([0] completed reductions, [1] error: 1 + r / 101 + r = rank r missing at
+ * entry / exit, [2] scratch).  avf_grad_allreduce sums the buckets of all ranks IN PLACE (every rank ends with the same bits: slice r
+ * is added up by rank r in rank order 0..W-1 and stored into all buckets); asynchronous on `stream`, graph-capturable, to be issued
+ * once per step on every rank; bounded spins (timeout_ns).  world <= 16, one node. */
+size_t avf_peer_allreduce_bytes(int32_t world, size_t n_floats);
+int avf_grad_allreduce(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns, void* stream);
+
 /* ---- parameter preparation ------------------------------------------------------------------ */
 int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

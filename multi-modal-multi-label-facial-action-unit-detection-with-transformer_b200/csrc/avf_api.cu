@@ -384,6 +384,16 @@ int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_
   return logits_wait(my_base, n_floats, world, state, timeout_ns, static_cast<cudaStream_t>(stream));
 }
 
+size_t avf_peer_allreduce_bytes(int32_t world, size_t n_floats) { return (world > 0 && world <= 16) ? peer_allreduce_bytes(world, n_floats) : 0; }
+
+int avf_grad_allreduce(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(peer_base && state, AVF_EINVAL, "grad_allreduce: null pointer");
+  AVF_REQUIRE(world > 0 && world <= 16 && rank >= 0 && rank < world && n_floats > 0, AVF_EINVAL, "grad_allreduce: world %d (1..16) rank %d n %zu", world, rank, n_floats);
+  return grad_allreduce(reinterpret_cast<const unsigned long long*>(peer_base), n_floats, world, rank, state, timeout_ns, static_cast<cudaStream_t>(stream));
+}
+
 int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
                             uint64_t* counts48, int32_t n_rows, void* stream) {
   int e = require_device();

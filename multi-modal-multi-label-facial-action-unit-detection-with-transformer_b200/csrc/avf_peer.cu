@@ -16,6 +16,8 @@
 //
 // Two slots are enough: A pushes step i+2 only after its wait of step i+1, which saw B's push of step i+1, which B issued (stream
 // order) after everything B did with the table of step i.  The spin is bounded (timeout -> error word, never a hung GPU).
+#include <algorithm>
+
 #include "avf_common.cuh"
 #include "avf_internal.h"
 
@@ -77,7 +79,122 @@ __global__ void logits_wait_kernel(const uint8_t* __restrict__ my_base, size_t n
   if (threadIdx.x == 0) state[0] = step + 1u;
 }
 
+// ---- gradient all-reduce (sum) of the flat fp32 bucket over peer memory -------------------------------------------------------
+// Training data parallelism: after the backward pass every rank holds its shard's gradient sum in a flat
+// bucket of n floats (41.7 MB for the hot path).  The bucket lives in a peer-mapped block, followed by two flag rows:
+//
+//     grad[n_pad] fp32 | enter[W] u32 | exit[W] u32            n_pad = n rounded up to a multiple of 4 * W
+//
+// One kernel, two-shot, in place: (1) tell every peer "my bucket is complete" and wait for theirs; (2) rank r sums slice r of all W
+// buckets (16-byte loads straight from the peers' memory, ranks added in the fixed order 0..W-1, so the result is deterministic and
+// identical everywhere) and stores the sum into slice r of ALL buckets; (3) tell every peer "my slice is in your bucket, I have stopped
+// reading yours" and wait for theirs.  Per GPU (W-1)/W of the bucket crosses NVLink once in each direction and nothing is staged,
+// against NCCL's ring / tree of the same 41.7 MB at 0.25 ms on 8 B200s.  Spins are bounded (timeout -> error word).
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t seq, unsigned long long timeout_ns) {
+  const unsigned long long t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (int32_t(ld_acquire_sys_u32(flag) - seq) < 0) {
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) return false;
+  }
+  return true;
+}
+
+constexpr int AR_THREADS = 256;
+constexpr int AR_MAX_WORLD = 16;
+
+// state: [0] sequence number of the last completed reduction, [1] error word, [2] CTAs of this launch that finished their slice
+template <int W>
+__global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsigned long long* __restrict__ peer_base, size_t n_pad, int world_rt, int rank,
+                                                                    uint32_t* state, unsigned long long timeout_ns) {
+  const int world = W > 0 ? W : world_rt;
+  const uint32_t seq = state[0] + 1u;
+  __shared__ unsigned long long base[AR_MAX_WORLD];
+  if (int(threadIdx.x) < world) base[threadIdx.x] = peer_base[threadIdx.x];
+  __syncthreads();
+  const size_t flag_off = n_pad * sizeof(float);
+  uint32_t* my_enter = reinterpret_cast<uint32_t*>(base[rank] + flag_off);
+  uint32_t* my_exit = my_enter + world;
+
+  // (1) my bucket is complete (stream order: the backward kernels are done); wait until everybody's is
+  if (blockIdx.x == 0 && int(threadIdx.x) < world) {
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(base[threadIdx.x] + flag_off) + rank, seq);
+  }
+  if (int(threadIdx.x) < world && !spin_until(my_enter + threadIdx.x, seq, timeout_ns)) atomicCAS(&state[1], 0u, 1u + threadIdx.x);
+  __syncthreads();
+
+  // (2) reduce my slice of all buckets, store it everywhere
+  const size_t slice4 = n_pad / 4 / world;
+  const size_t lo4 = slice4 * rank;
+  constexpr int NW = W > 0 ? W : AR_MAX_WORLD;          // loads per element
+  constexpr int U = NW >= 8 ? 1 : 8 / NW;               // elements per thread and trip: eight 16-byte loads in flight whatever W is
+  const size_t stride = size_t(gridDim.x) * AR_THREADS;
+  for (size_t i0 = size_t(blockIdx.x) * AR_THREADS + threadIdx.x; i0 < slice4; i0 += stride * U) {
+    float4 v[U][NW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+#pragma unroll
+      for (int r = 0; r < NW; ++r)
+        if (r < world && i < slice4) v[u][r] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(base[r]) + lo4 + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i >= slice4) break;
+      float4 acc = v[u][0];
+#pragma unroll
+      for (int r = 1; r < NW; ++r)
+        if (r < world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
+#pragma unroll
+      for (int r = 0; r < NW; ++r)
+        if (r < world) reinterpret_cast<float4*>(base[r])[lo4 + i] = acc;
+    }
+  }
+  __syncthreads();
+
+  // (3) the last CTA of this rank to finish tells every peer; CTA 0 waits for everybody's slice to have landed here
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const uint32_t prev = atomicAdd(&state[2], 1u);
+    if (prev == gridDim.x - 1) {
+      state[2] = 0;
+      __threadfence_system();
+      for (int p = 0; p < world; ++p) st_release_sys_u32(reinterpret_cast<uint32_t*>(base[p] + flag_off) + world + rank, seq);
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (int(threadIdx.x) < world && !spin_until(my_exit + threadIdx.x, seq, timeout_ns)) atomicCAS(&state[1], 0u, 101u + threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) state[0] = seq;
+  }
+}
+
 }  // namespace
+
+size_t peer_allreduce_pad(int world, size_t n) { return (n + size_t(4) * world - 1) / (size_t(4) * world) * (size_t(4) * world); }
+size_t peer_allreduce_bytes(int world, size_t n) { return peer_allreduce_pad(world, n) * sizeof(float) + size_t(2) * world * sizeof(uint32_t); }
+
+int grad_allreduce(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, cudaStream_t st) {
+  const size_t n_pad = peer_allreduce_pad(world, n);
+  const size_t slice4 = n_pad / 4 / world;
+  int grid = int(std::min<size_t>(size_t(sm_count_of_current_device()), (slice4 + AR_THREADS - 1) / AR_THREADS));
+  if (grid < 1) grid = 1;
+  switch (world) {
+    case 2: grad_allreduce_kernel<2><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
+    case 4: grad_allreduce_kernel<4><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
+    case 8: grad_allreduce_kernel<8><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
+    default: grad_allreduce_kernel<0><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
+  }
+  AVF_LAUNCH_CHECK("grad_allreduce_kernel");
+  return 0;
+}
 
 size_t peer_gather_bytes(int world, size_t n) { return peer_flags_offset(world, n) + size_t(2) * world * sizeof(uint32_t); }
 

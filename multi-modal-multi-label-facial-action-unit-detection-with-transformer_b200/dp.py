@@ -159,6 +159,56 @@ class PeerLogitGather:
             raise RuntimeError(f"PeerLogitGather: device step counter {step} != host count {self.done} (missing note_replay()?)")
 
 
+class PeerAllReduce:
+    """The gradient all-reduce of data-parallel training as ONE kernel over NVLink peer memory (csrc/avf_peer.cu,
+    avf_grad_allreduce): the flat fp32 gradient bucket lives in a peer-mapped block (``.grad``, n floats); ``reduce_()`` sums the
+    buckets of all ranks in place — rank r adds up slice r straight from the peers' memory, in rank order, and stores it into every
+    bucket, so all ranks end with identical bits and the result does not depend on timing.  Asynchronous on the current stream,
+    graph-capturable, issued once per step on every rank.  Sums only; the optimiser folds 1 / world into its update."""
+
+    def __init__(self, n_floats: int, device=None, group=None, timeout_s: float = 10.0):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerAllReduce needs an initialised torch.distributed process group (NCCL, one node)")
+        self._ct, self._L = ctypes, _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 16:
+            raise RuntimeError("PeerAllReduce: at most 16 ranks (one NVLink domain)")
+        self.n = int(n_floats)
+        self.timeout_ns = int(timeout_s * 1e9)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(_lib.lib().avf_peer_allreduce_bytes(self.world, self.n))
+        self.block = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        self.block.zero_()
+        self.handle = symm.rendezvous(self.block, self.group)
+        ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.block.data_ptr():
+            raise RuntimeError("PeerAllReduce: symmetric-memory rendezvous returned an unexpected pointer table")
+        self.peer_base = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+        self.state = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.grad = self.block[:self.n]
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+
+    def reduce_(self) -> torch.Tensor:
+        c = self._ct.c_void_p
+        self._L.check(self._L.lib().avf_grad_allreduce(c(self.peer_base.data_ptr()), self.n, self.world, self.rank, c(self.state.data_ptr()),
+                                                       self.timeout_ns, c(torch.cuda.current_stream().cuda_stream)), "avf_grad_allreduce")
+        return self.grad
+
+    def check(self) -> int:
+        """Synchronise; raise if a peer never showed up; return the number of completed reductions."""
+        torch.cuda.synchronize()
+        done, err = (int(v) for v in self.state[:2].tolist())
+        if err != 0:
+            who, where = ((err - 1), "entry") if err < 100 else ((err - 101), "exit")
+            raise RuntimeError(f"PeerAllReduce: rank {who} did not reach the {where} of the reduction within {self.timeout_ns / 1e9:.1f} s")
+        return done
+
+
 class SegmentReducer:
     """Gradient all-reduce overlapped with the backward pass.  The flat gradient bucket is laid out in contiguous segments, one
     per stack, in the order the stacks finish their backward (optim.FusedAdam).  ``ready(params)`` is called whenever the kernels

@@ -34,7 +34,7 @@ from .dp import SegmentReducer
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  decoupled: bool = False, process_group=None, segments: Optional[Sequence[Sequence[torch.nn.Parameter]]] = None,
-                 overlap: Optional[bool] = None):
+                 overlap: Optional[bool] = None, reduce: Optional[str] = None):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("FusedAdam: invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled))
@@ -55,6 +55,13 @@ class FusedAdam(torch.optim.Optimizer):
         # overlap=True turns it on (the data-parallel parity check, bench.py --check, always exercises it).
         self.overlap = (os.environ.get("AVF_OVERLAP_REDUCE", "0") == "1") if overlap is None else bool(overlap)
         self._reducer: Optional[SegmentReducer] = None
+        # how the flat bucket is summed across ranks when the reduction is not overlapped: "peer" = one kernel over NVLink peer memory
+        # (dp.PeerAllReduce; the bucket is then allocated from torch symmetric memory), "nccl" = dist.all_reduce.  AVF_GRAD_REDUCE
+        # overrides; "peer" falls back to "nccl" (on all ranks together) where no peer mapping is available, see reduce_note.
+        self.reduce_mode = os.environ.get("AVF_GRAD_REDUCE", "peer") if reduce is None else str(reduce)
+        if self.reduce_mode not in ("peer", "nccl"):
+            raise ValueError("FusedAdam: reduce must be 'peer' or 'nccl'")
+        self.reduce_note = None
         self._listening = False
         weakself = weakref.ref(self)
 
@@ -76,7 +83,8 @@ class FusedAdam(torch.optim.Optimizer):
             offs.append(n)
             n += (p.numel() + 7) // 8 * 8            # 32-byte aligned in the fp32 bucket, 16-byte (TMA) aligned in the bf16 shadow
         flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        peer = self._peer_bucket(n, dev)
+        flat_g = peer.grad if peer is not None else torch.zeros(n, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for p, o in zip(params, offs):
                 flat_p[o:o + p.numel()].copy_(p.detach().reshape(-1))
@@ -100,7 +108,7 @@ class FusedAdam(torch.optim.Optimizer):
                     seg_of[id(q)] = si
         self._seg_of = seg_of
         self._n_seg = len(bounds)
-        b = dict(params=params, offs=offs, p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
+        b = dict(params=params, offs=offs, p=flat_p, g=flat_g, peer=peer, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
                  bounds=bounds, counts=counts)
         # moments restored by load_state_dict before the bucket existed (torch keeps them in self.state until then)
         with torch.no_grad():
@@ -112,6 +120,23 @@ class FusedAdam(torch.optim.Optimizer):
                     b["step"] = max(b["step"], int(st["step"]))
                     self.state.pop(p)
         return b
+
+    def _peer_bucket(self, n: int, dev):
+        """The gradient bucket as a peer-mapped block (collective: every rank builds its bucket in its first step())."""
+        if self._world() == 1 or self.reduce_mode != "peer":
+            return None
+        from .dp import PeerAllReduce
+        peer = None
+        try:
+            peer = PeerAllReduce(n, device=dev, group=self.process_group)
+        except Exception as ex:
+            self.reduce_note = f"peer-memory all-reduce unavailable ({type(ex).__name__}: {str(ex)[:160]}); NCCL all-reduce instead"
+        agree = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.process_group)
+        if int(agree.item()) == 0:
+            self.reduce_mode = "nccl"
+            return None
+        return peer
 
     # -- checkpointing: torch.optim.Adam's state layout (step / exp_avg / exp_avg_sq per parameter) ------------------------------
     def state_dict(self):
@@ -226,6 +251,8 @@ class FusedAdam(torch.optim.Optimizer):
             if world > 1 and self._reducer is not None and self._reducer.armed:
                 self._reducer.finish()                            # segments were armed for this backward pass: reduce / join what is left
                 self._reducer.disarm()
+            elif world > 1 and b.get("peer") is not None:
+                b["peer"].reduce_()                               # one kernel over NVLink peer memory, in place
             elif world > 1:
                 dist.all_reduce(b["g"], op=dist.ReduceOp.SUM, group=self.process_group)
             b["step"] += 1
