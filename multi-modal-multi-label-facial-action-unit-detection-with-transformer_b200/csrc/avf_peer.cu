@@ -90,11 +90,10 @@ __global__ void logits_wait_kernel(const uint8_t* __restrict__ my_base, size_t n
 // identical everywhere) and stores the sum into slice r of ALL buckets; (3) tell every peer "my slice is in your bucket, I have stopped
 // reading yours" and wait for theirs.  Per GPU (W-1)/W of the bucket crosses NVLink once in each direction and nothing is staged,
 // against NCCL's ring / tree of the same 41.7 MB at 0.25 ms on 8 B200s.  Spins are bounded (timeout -> error word).
-__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
+// Bucket loads: weak ld.global.cg (L2 only).  They are ordered behind the acquire of the peers' "bucket complete" flags (ld.acquire.sys
+// + bar.sync), which is all the memory model asks for, and — unlike volatile / .relaxed.sys loads, which ptxas issued in dependent
+// groups of 4 + 2 + 2 — the eight of them go out back to back, one NVLink round trip per element.
+__device__ __forceinline__ float4 ld_bucket_f4(const float4* p) { return __ldcg(p); }
 
 __device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t seq, unsigned long long timeout_ns) {
   const unsigned long long t0 = global_timer_ns();
@@ -135,6 +134,9 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
   constexpr int NW = W > 0 ? W : AR_MAX_WORLD;          // loads per element
   constexpr int U = NW >= 8 ? 1 : 8 / NW;               // elements per thread and trip: eight 16-byte loads in flight whatever W is
   const size_t stride = size_t(gridDim.x) * AR_THREADS;
+  float4* buck[NW];                                     // slice `rank` of every bucket, in registers
+#pragma unroll
+  for (int r = 0; r < NW; ++r) buck[r] = reinterpret_cast<float4*>(base[r < world ? r : 0]) + lo4;
   for (size_t i0 = size_t(blockIdx.x) * AR_THREADS + threadIdx.x; i0 < slice4; i0 += stride * U) {
     float4 v[U][NW];
 #pragma unroll
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
       const size_t i = i0 + u * stride;
 #pragma unroll
       for (int r = 0; r < NW; ++r)
-        if (r < world && i < slice4) v[u][r] = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(base[r]) + lo4 + i);
+        if (r < world && i < slice4) v[u][r] = ld_bucket_f4(buck[r] + i);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
         if (r < world) { acc.x += v[u][r].x; acc.y += v[u][r].y; acc.z += v[u][r].z; acc.w += v[u][r].w; }
 #pragma unroll
       for (int r = 0; r < NW; ++r)
-        if (r < world) reinterpret_cast<float4*>(base[r])[lo4 + i] = acc;
+        if (r < world) buck[r][i] = acc;
     }
   }
   __syncthreads();
@@ -184,7 +186,9 @@ size_t peer_allreduce_bytes(int world, size_t n) { return peer_allreduce_pad(wor
 int grad_allreduce(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, cudaStream_t st) {
   const size_t n_pad = peer_allreduce_pad(world, n);
   const size_t slice4 = n_pad / 4 / world;
-  int grid = int(std::min<size_t>(size_t(sm_count_of_current_device()), (slice4 + AR_THREADS - 1) / AR_THREADS));
+  // two CTAs per SM: ptxas keeps four of a thread's eight 16-byte loads in flight at a time, so the bytes in flight (2 x 148 x 256 x 64 B =
+  // 4.8 MB) come from the CTA count; all of them are co-resident (<= 128 registers, 128 B of shared memory), as the flag protocol needs
+  int grid = int(std::min<size_t>(size_t(2 * sm_count_of_current_device()), (slice4 + AR_THREADS - 1) / AR_THREADS));
   if (grid < 1) grid = 1;
   switch (world) {
     case 2: grad_allreduce_kernel<2><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;

@@ -469,6 +469,19 @@ def test_graphed_hot_path_with_the_logit_gather_inside_the_graph():
         lone.wait()
         with pytest.raises(RuntimeError, match="rank 0 did not arrive"):
             lone.check()
+
+        # the gradient all-reduce kernel on a one-rank communicator: the sum over one bucket is the bucket (ragged length: padding and
+        # flag rows behind it stay out of the way), twice in a row (sequence numbers), and FusedAdam takes its bucket from it
+        ar = A.dp.PeerAllReduce(100003)
+        ar.grad.copy_(torch.randn(100003, device="cuda"))
+        before = ar.grad.clone()
+        ar.reduce_()
+        ar.reduce_()
+        assert ar.check() == 2 and torch.equal(ar.grad, before)
+        m.train()
+        params = [q for q in m.au_head.parameters() if q.requires_grad]
+        opt = A.FusedAdam(params, lr=1e-3)
+        assert opt.reduce_mode == "peer"
     finally:
         dist.destroy_process_group()
 
