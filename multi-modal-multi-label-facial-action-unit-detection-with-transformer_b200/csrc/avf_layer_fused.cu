@@ -10,11 +10,15 @@
 //   * attention is per head on the tensor cores: [Q|K|V]_h = LN(x) Wqkv_h^T (N=96), S = Q K^T over the whole tile
 //     (block-diagonal: a row only uses the columns of its own sequence), softmax in registers, P written back as
 //     bf16 INTO the S columns of TMEM and used as the A operand of O = P V (V is an MN-major B operand);
-//   * the out-projection runs PER HEAD (x += O_h Wout[:, 32h:32h+32]^T, N = 256, K = 32) as soon as O_h is normalised, so
-//     there is no attention-output buffer: during the attention phase the 64 KB of A1 hold the O_h staging (2 x 8 KB) and a
-//     second weight ring of 4 x 12 KB = one whole head of [Wq_h; Wk_h; Wv_h], so QKV(h+1) never waits for L2;
-//   * the other weights are streamed from L2 by TMA through a 3-slot ring, activations enter / leave as whole NCHW frames
-//     by bulk copies (SFormer, models/vformer.py:245-259) or as fp32 rows.
+//   * the out-projection runs PER HEAD (x += O_h Wout[:, 32h:32h+32]^T, N = 256, K = 32) as soon as O_h is normalised: O_h / l is
+//     written back over its own accumulator columns as packed bf16 and is the TMEM A operand of that GEMM (no attention-output
+//     buffer, no proxy fence); [Wq_h; Wk_h; Wv_h] arrive through their own ring of 6 x 12 KB (one and a half heads in flight, one
+//     "head full" barrier per head), so QKV(h+1) never waits for L2;
+//   * the other weights are streamed from L2 by TMA through 16 KB slots (two during attention, nine in the MLP phase, when the
+//     Q/K/V staging and the QKV ring are idle; one barrier per group of four), activations enter / leave as whole NCHW frames
+//     by bulk copies (SFormer, models/vformer.py:245-259) or as fp32 rows;
+//   * tiles are handed out by an atomic counter (NCHW form): the weight producer fetches the next index one tile ahead and
+//     publishes it to the other roles through a four-entry queue in shared memory (see next_tile).
 //
 // Warp roles: 0 = TMA producer (out-proj / MLP weights; also the next tile's input frames), 1 = TMEM allocator + MMA issuer
 // (one thread), 2 = TMA producer of the QKV ring, 3.. = row workers (warp w owns TMEM lanes 32*(w%4)..+31; the NSPLIT warps
