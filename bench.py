@@ -364,7 +364,7 @@ def run_ours(args):
         peer, gather_note = None, None
         if gather_mode == "peer":
             try:
-                peer = A.dp.PeerLogitGather(B, 21)
+                peer = A.dp.PeerLogitGather(B, 21, timeout_s=30.0)
             except Exception as ex:                 # no peer mapping on this box (symmetric memory unavailable): NCCL in the stream instead, and say so
                 gather_note = f"peer-memory gather unavailable ({type(ex).__name__}: {str(ex)[:160]}); NCCL all-gather in the stream instead"
             agree = torch.tensor([1 if peer is not None else 0], device=dev)

@@ -166,7 +166,7 @@ class PeerAllReduce:
     bucket, so all ranks end with identical bits and the result does not depend on timing.  Asynchronous on the current stream,
     graph-capturable, issued once per step on every rank.  Sums only; the optimiser folds 1 / world into its update."""
 
-    def __init__(self, n_floats: int, device=None, group=None, timeout_s: float = 10.0):
+    def __init__(self, n_floats: int, device=None, group=None, timeout_s: float = 30.0):
         import ctypes
         import torch.distributed._symmetric_memory as symm
         from . import _lib

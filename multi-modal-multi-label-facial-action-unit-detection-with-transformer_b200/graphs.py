@@ -19,15 +19,43 @@ from . import _lib
 from .encoder import Transformer
 
 
-def weights_signature(model) -> tuple:
-    """Changes whenever a parameter or buffer of ``model`` may have changed: the optimiser epoch (FusedAdam writes parameters
-    through raw pointers) plus every tensor's version counter and address (load_state_dict, in-place edits, .to()).  A captured
-    graph holds raw pointers to the PACKED (bf16 / stacked / BN-folded) copies of the weights, which the eager path re-packs —
-    and frees — on such a change: a graph replayed afterwards would read stale weights or recycled memory."""
+def hot_path_modules(model) -> list:
+    """The sub-modules whose weights the transformer hot path reads: SFormer stack, TFormer, the two AU_formers,
+    the fusion head — flattened to the list of modules that own parameters or buffers.  Conv backbones are not among them."""
+    vm = model.video_model.video_model
+    roots = [vm.s_former, vm.t_former, model.video_model.au_head, model.audio_model.au_head, model.au_head]
+    mods = []
+    for r in roots:
+        for mod in r.modules():
+            if isinstance(mod, torch.nn.Conv2d) or isinstance(mod, torch.nn.BatchNorm2d):
+                continue                                   # the conv stages inside SFormer's wrapper stay torch modules outside the path
+            if mod._parameters or mod._buffers:
+                mods.append(mod)
+    return mods
+
+
+def weights_signature(model, modules: Optional[list] = None) -> tuple:
+    """Changes whenever a parameter or buffer may have changed: the optimiser epoch (FusedAdam writes parameters through raw
+    pointers) plus every tensor's version counter, per-parameter update count and address (load_state_dict, in-place edits, .to(),
+    a replaced Parameter object).  A captured graph holds raw pointers to the PACKED (bf16 / stacked / BN-folded) copies of the
+    weights, which the eager path re-packs — and frees — on such a change: a graph replayed afterwards would read stale weights or
+    recycled memory.
+
+    ``modules`` = the modules to watch (default: every module of ``model``).  This runs on the host in front of EVERY graph replay:
+    the full model's 600 tensors cost about 0.9 ms per call — as long as the whole 1.09 ms forward step, so the replay loop became
+    host-bound on a slower host (1.40 ms per step measured) — which is why GraphedHotPath watches only the hot path's modules,
+    through their ``_parameters`` / ``_buffers`` dicts directly (no module-tree walk, no generator chain)."""
     from . import functional as AF
+    if modules is None:
+        modules = list(model.modules())
     v = 0
-    for t in list(model.parameters()) + list(model.buffers()):
-        v = (v * 1000003 + (t._version + getattr(t, "_avf_wver", 0)) * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+    for mod in modules:
+        for t in mod._parameters.values():
+            if t is not None:
+                v = (v * 1000003 + (t._version + getattr(t, "_avf_wver", 0)) * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        for t in mod._buffers.values():
+            if t is not None:
+                v = (v * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
     return (AF.WEIGHTS_EPOCH, v)
 
 
@@ -96,7 +124,8 @@ class GraphedHotPath:
             with torch.cuda.graph(self.graph):
                 self.out = self._run()
         self._keep = _packed_refs(self.model)          # the graph reads these through raw pointers
-        self._sig = weights_signature(self.model)
+        self._watch = hot_path_modules(self.model)
+        self._sig = weights_signature(self.model, self._watch)
 
     def _run(self):
         m = self.model
@@ -159,7 +188,7 @@ class GraphedHotPath:
             self.frame.copy_(frame, non_blocking=True)
         if audio is not None and audio.data_ptr() != self.audio.data_ptr():
             self.audio.copy_(audio, non_blocking=True)
-        if weights_signature(self.model) != self._sig:   # optimizer.step(), load_state_dict(), in-place edits: re-pack and capture again
+        if weights_signature(self.model, self._watch) != self._sig:   # optimizer.step(), load_state_dict(), in-place edits: re-pack and capture again
             if self.model.training:
                 raise RuntimeError("GraphedHotPath captures the inference kernels: call model.eval() first")
             self.recaptures += 1
