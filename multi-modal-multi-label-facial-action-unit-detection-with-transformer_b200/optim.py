@@ -93,6 +93,7 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = flat_g[o:o + p.numel()].view(p.shape)
                 p._avf_direct_grad = True           # autograd.direct_grad_ok: the backward kernels may accumulate into this view
         shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)       # bf16 copy of the bucket, refreshed by the update kernel
+        shadow_views = {id(p): shadow[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs) if p.dim() >= 2}
         bounds, counts = [], []                                          # [lo, hi) of each non-empty segment in the bucket
         for si in range(self._n_seg + 1):
             idx = [i for i, q in enumerate(params) if self._seg_of.get(id(q), self._n_seg) == si]
@@ -108,7 +109,11 @@ class FusedAdam(torch.optim.Optimizer):
                     seg_of[id(q)] = si
         self._seg_of = seg_of
         self._n_seg = len(bounds)
-        b = dict(params=params, offs=offs, p=flat_p, g=flat_g, peer=peer, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
+        # host-side caches for step(): per-parameter gradient views / addresses and the bf16 shadow views of the weight matrices
+        g_views = [flat_g[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+        b_extra = dict(ids=frozenset(id(p) for p in params), g_views=g_views, g_ptrs=[v.data_ptr() for v in g_views],
+                       mats=[(p, shadow_views[id(p)]) for p in params if p.dim() >= 2])
+        b = dict(params=params, offs=offs, p=flat_p, g=flat_g, peer=peer, **b_extra, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), shadow=shadow, step=0,
                  bounds=bounds, counts=counts)
         # moments restored by load_state_dict before the bucket existed (torch keeps them in self.state until then)
         with torch.no_grad():
@@ -210,14 +215,14 @@ class FusedAdam(torch.optim.Optimizer):
     def _zero_grad(self, set_to_none: bool = True) -> None:
         for gi, group in enumerate(self.param_groups):
             b = self._buckets[gi]
-            bucketed = set()
+            bucketed = frozenset()
             if b is not None:
                 b["g"].zero_()
-                for p, o in zip(b["params"], b["offs"]):
-                    view = b["g"][o:o + p.numel()].view(p.shape)
-                    if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                for p, view, ptr in zip(b["params"], b["g_views"], b["g_ptrs"]):
+                    g = p.grad
+                    if g is None or g.data_ptr() != ptr:
                         p.grad = view
-                    bucketed.add(id(p))
+                bucketed = b["ids"]
             for p in group["params"]:
                 if id(p) in bucketed or p.grad is None:
                     continue
@@ -234,18 +239,26 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         world = self._world()
         for gi, group in enumerate(self.param_groups):
-            with_grad = [p for p in group["params"] if p.grad is not None]
-            if not with_grad:
-                continue
             b = self._buckets[gi]
-            if b is None or {id(p) for p in b["params"]} != {id(p) for p in with_grad}:
-                if b is not None:
-                    raise RuntimeError("FusedAdam: the set of parameters receiving gradients changed after the first step")
+            if b is None:
+                with_grad = [p for p in group["params"] if p.grad is not None]
+                if not with_grad:
+                    continue
                 b = self._buckets[gi] = self._flatten(with_grad)
             else:
-                for p, o in zip(b["params"], b["offs"]):          # a gradient that autograd re-allocated: pull it into the bucket
-                    view = b["g"][o:o + p.numel()].view(p.shape)
-                    if p.grad.data_ptr() != view.data_ptr():
+                # steady state: this runs on the host in front of every update, so no tensor is created here (cached views / addresses)
+                ids, n_with = b["ids"], 0
+                for p in group["params"]:
+                    if p.grad is not None:
+                        n_with += 1
+                        if id(p) not in ids:
+                            raise RuntimeError("FusedAdam: the set of parameters receiving gradients changed after the first step")
+                if n_with == 0:
+                    continue
+                if n_with != len(ids):
+                    raise RuntimeError("FusedAdam: the set of parameters receiving gradients changed after the first step")
+                for p, view, ptr in zip(b["params"], b["g_views"], b["g_ptrs"]):   # a gradient that autograd re-allocated: pull it into the bucket
+                    if p.grad.data_ptr() != ptr:
                         view.copy_(p.grad)
                         p.grad = view
             if world > 1 and self._reducer is not None and self._reducer.armed:
@@ -260,9 +273,8 @@ class FusedAdam(torch.optim.Optimizer):
                           group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world, shadow=b["shadow"])
             # GEMM operand copies for free: weight matrices point at their bf16 image in the shadow bucket, valid for exactly this
             # parameter version (load_state_dict / manual edits bump the version and fall back to the cast kernel)
-            for p, o in zip(b["params"], b["offs"]):
-                if p.dim() >= 2:
-                    p._avf_bf16 = (b["shadow"][o:o + p.numel()].view(p.shape), p._version)
+            for p, sview in b["mats"]:
+                p._avf_bf16 = (sview, p._version)
             for p in b["params"]:                               # per-parameter staleness: packed copies of OTHER (frozen) parameters stay valid
                 p._avf_wver = getattr(p, "_avf_wver", 0) + 1
         return loss
