@@ -103,13 +103,25 @@ constexpr int SMEM_USED = OFF_BAR + 512;
 constexpr int SMEM_ALLOC = SMEM_USED + 1024;       // slack for the 1024-byte alignment of the base
 static_assert(SMEM_ALLOC <= 232448, "shared memory budget");
 
+// K-panel order of the two GEMMs that read a fresh LayerNorm output (QKV, FF1).  The two threads of a row write panels {0,1} and {2,3}
+// of A0, so panels 0 and 2 are complete when every thread is half-way through its normalisation sweep (B_A0_HALF): the first GEMM behind
+// a LayerNorm starts on them and only then waits for the whole operand (B_A0_READY).  AVF_A0_HALF=0: plain order, one barrier.
+#ifndef AVF_A0_HALF
+#define AVF_A0_HALF 1
+#endif
+#if AVF_A0_HALF
+__device__ __forceinline__ constexpr int kpanel(int i) { return ((i & 1) << 1) | (i >> 1); }      // 0, 2, 1, 3
+#else
+__device__ __forceinline__ constexpr int kpanel(int i) { return i; }
+#endif
+
 // TMEM columns
 constexpr uint32_t TM_X = 0, TM_D1 = 256, TM_O = 352, TM_S = 384, TM_H0 = 256, TM_H1 = 384;
 
 enum {
   B_RING_FULL = 0, B_RING_EMPTY = RING, B_X0_FULL = 2 * RING, B_A0_FREE, B_A0_READY, B_D1_FULL, B_STAGED, B_S_FULL, B_P_READY, B_O_FULL,
   B_O_DRAINED, B_X1_FULL, B_HACC_FULL, B_HACC_FULL1, B_H_READY, B_H_READY1, B_X2_FULL,
-  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, B_TQ_FULL = B_G_FULL + 8, NUM_BARS = B_TQ_FULL + 4
+  B_QG_FULL, B_QR_EMPTY = B_QG_FULL + 2, B_A1_FREE = B_QR_EMPTY + QRING, B_OUT_READ, B_QKV_FREE, B_G_FULL, B_TQ_FULL = B_G_FULL + 8, B_A0_HALF = B_TQ_FULL + 4, NUM_BARS
 };
 static_assert(NUM_BARS * 8 + 8 + 16 <= 512, "barrier block (+ TMEM slot + tile queue)");
 
@@ -288,6 +300,9 @@ struct Worker {
         f2_unpack(f2_add(f2_pack(x[j + 2], x[j + 3]), b.y), x[j + 2], x[j + 3]);
       }
       tmem_st32(tl + TM_X + col0, reinterpret_cast<const uint32_t(&)[32]>(x));
+#if AVF_A0_HALF
+      if (c0 == 32) arrive(B_A0_HALF);          // this thread's first panel (0 or 2) is written
+#endif
     }
     tmem_st_wait();
     arrive(B_A0_READY);
@@ -850,7 +865,7 @@ __device__ void producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars)
       auto ff1 = [&](int c) {
         for (int kp = 0; kp < 4; ++kp) {
           if (kp % MLPG == 0) ++gidx;
-          load((m++) % RING, &L.tm_w1, kp * 64, c * 128, &bars[B_G_FULL + ((gidx - 1) & 7u)], kp % MLPG == 0 ? MLPG * SLOT_BYTES : 0);
+          load((m++) % RING, &L.tm_w1, kpanel(kp) * 64, c * 128, &bars[B_G_FULL + ((gidx - 1) & 7u)], kp % MLPG == 0 ? MLPG * SLOT_BYTES : 0);
         }
       };
       auto ff2 = [&](int c) {
@@ -896,7 +911,7 @@ __device__ void qkv_producer_main(const FusedArgs& a, uint8_t* smem, uint64_t* b
           mbar_wait(&bars[B_QR_EMPTY + s], ph ^ 1);
           uint8_t* d = smem + OFF_QRING + s * QSLOT_BYTES;
           if (kp == 0) mbar_expect_tx(fb, 4 * QSLOT_BYTES);
-          for (int s3 = 0; s3 < 3; ++s3) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kp * 64, s3 * (HEADS * DH) + h * DH);
+          for (int s3 = 0; s3 < 3; ++s3) tma_load_2d(d + s3 * 4096, &L.tm_qkv, fb, kpanel(kp) * 64, s3 * (HEADS * DH) + h * DH);
           ++qit;
         }
       }
@@ -939,17 +954,34 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   auto slot_release = [&](uint32_t s) {
     if (leader) umma_commit(&bars[B_RING_EMPTY + s]);
   };
-  auto qkv = [&]() {                          // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T, weights from the QKV ring
+  // fresh = the first GEMM behind a LayerNorm: its first two panels (0, 2) only need B_A0_HALF, the other two B_A0_READY
+  auto a0_wait = [&](int i, bool fresh) {
+#if AVF_A0_HALF
+    if (!fresh || (i != 0 && i != 2)) return;
+    pf.mark(ring_phase);
+    if (i == 0) mbar_wait(&bars[B_A0_HALF], n_a0 & 1);
+    else mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
+#else
+    if (!fresh || i != 0) return;
+    pf.mark(ring_phase);
+    mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
+#endif
+    tc_fence_after();
+    pf.mark(ring_phase == PM_QKV ? PM_WAIT_A0 : PM_WAIT_A0B);
+  };
+  auto qkv = [&](bool fresh) {                // D1[128 x 96] = LN(x) [Wq_h; Wk_h; Wv_h]^T, weights from the QKV ring
     pf.mark(ring_phase);
     mbar_wait(&bars[B_QG_FULL + (hq & 1u)], (hq >> 1) & 1u);      // all four panels of the head
     ++hq;
     tc_fence_after();
     pf.mark(PM_RW_QKV);
-    for (int kp = 0; kp < 4; ++kp) {
+    for (int i = 0; i < 4; ++i) {
+      const int kp = kpanel(i);
+      a0_wait(i, fresh);
       const uint32_t s = qit % QRING;
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(qring + s * QSLOT_BYTES);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (kp | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(tmem + TM_D1, da + uint64_t(k * 2), db + uint64_t(k * 2), id_qkv, (i | k) != 0 ? 1u : 0u);
       if (leader) umma_commit(&bars[B_QR_EMPTY + s]);
       ++qit;
     }
@@ -969,14 +1001,16 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
     slot_release(s);
   };
   bool last_layer = false;
-  auto ff1 = [&](int c) {                     // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
+  auto ff1 = [&](int c, bool fresh) {         // H[c&1][128 x 128] = LN2(x) W1[c*128.., :]^T
     const uint32_t d = tmem + ((c & 1) ? TM_H1 : TM_H0);
-    for (int kp = 0; kp < 4; ++kp) {
-      if (kp % MLPG == 0) group_wait();
+    for (int i = 0; i < 4; ++i) {
+      const int kp = kpanel(i);
+      if (i % MLPG == 0) group_wait();
+      a0_wait(i, fresh);
       const uint32_t s = (m++) % RING, sb = smem0 + uint32_t(slot_offset(s));
       const uint64_t da = make_desc_sw128_kmajor(a0 + kp * 16384), db = make_desc_sw128_kmajor(sb);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (kp | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) if (leader) umma_bf16(d, da + uint64_t(k * 2), db + uint64_t(k * 2), id_128, (i | k) != 0 ? 1u : 0u);
       slot_release(s);
     }
     if (leader) umma_commit(&bars[B_HACC_FULL + (c & 1)]);
@@ -986,11 +1020,8 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
   for (uint32_t tk = 0; next_tile(bars, tk) >= 0; ++tk) {
     for (int l = 0; l < a.depth; ++l) {
       last_layer = l == a.depth - 1;
-      mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
-      tc_fence_after();
-      pf.mark(PM_WAIT_A0);
       ring_phase = PM_QKV;
-      qkv();
+      qkv(true);                              // (the waits for LayerNorm 1's output are inside)
       pf.mark(PM_QKV);
       for (int h = 0; h < HEADS; ++h) {
         mbar_wait(&bars[B_STAGED], h & 1);
@@ -1003,7 +1034,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
           if (leader) umma_commit(&bars[B_S_FULL]);
         }
         pf.mark(PM_S);
-        if (h + 1 < HEADS) qkv();
+        if (h + 1 < HEADS) qkv(false);
         pf.mark(PM_QKV);
         if (h > 0) {                          // O(h-1) is out of TMEM and staged: its slice of the out-projection
           mbar_wait(&bars[B_O_DRAINED], (h - 1) & 1);
@@ -1032,12 +1063,9 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
       m = 0;
       pf.mark(PM_OUT);
 
-      mbar_wait(&bars[B_A0_READY], (n_a0++) & 1);
-      tc_fence_after();
-      pf.mark(PM_WAIT_A0B);
       ring_phase = PM_FF1;
-      ff1(0);
-      if (a.n_chunks > 1) ff1(1);
+      ff1(0, true);                           // (the waits for LayerNorm 2's output are inside)
+      if (a.n_chunks > 1) ff1(1, false);
       for (int c = 0; c < a.n_chunks; ++c) {
         const int b = c & 1;
         pf.mark(PM_FF1);
@@ -1057,7 +1085,7 @@ __device__ void mma_main(const FusedArgs& a, uint8_t* smem, uint64_t* bars, uint
           }
         pf.mark(PM_FF2);
         ring_phase = PM_FF1;
-        if (c + 2 < a.n_chunks) ff1(c + 2);     // overwrites H_c: in order behind the MMAs above that read it
+        if (c + 2 < a.n_chunks) ff1(c + 2, false);     // overwrites H_c: in order behind the MMAs above that read it
       }
       if (leader) umma_commit(&bars[B_X2_FULL]);
       if (leader) umma_commit(&bars[B_A1_FREE]);
@@ -1090,7 +1118,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) encoder_fused_kernel(const __g
       tma_prefetch_desc(&a.layer[l].tm_w2);
     }
     for (int i = 0; i < NUM_BARS; ++i) {
-      const bool by_workers = i == B_A0_READY || i == B_STAGED || i == B_P_READY || i == B_O_DRAINED || i == B_H_READY || i == B_H_READY1;
+      const bool by_workers = i == B_A0_READY || i == B_A0_HALF || i == B_STAGED || i == B_P_READY || i == B_O_DRAINED || i == B_H_READY || i == B_H_READY1;
       mbar_init(&bars[i], by_workers ? NUM_WORKERS / 32 : 1);
     }
     fence_barrier_init();
