@@ -87,12 +87,13 @@ constexpr int OFF_K = OFF_Q + 8192;                // 8 KB   K_h
 constexpr int OFF_V = OFF_K + 8192;                // 2x8 KB V_h [128 tok x 32] MN-major SW64, double buffered
 constexpr int OFF_RING = OFF_V + 16384;            // 2 x 16 KB weight ring (slots 2-3; slots 0-1 = the 32 KB of Q/K/V staging above)
 constexpr int OFF_OST = OFF_RING + (RING_HI - RING_LO) * SLOT_BYTES;   // 8 KB  O_h / l  [128 x 32] K-major SW64 (single: out-proj(h-1) is issued before PV(h))
-constexpr int OFF_QRING = OFF_OST + 8192;          // QRING x 12 KB QKV weight ring; also the NCHW output staging (2 x 64 x 256 bf16 at most)
+constexpr int OFF_QRING = OFF_OST + (AVF_O_TMEM ? 0 : 8192);   // QRING x 12 KB QKV weight ring (right behind slot 3 when O_h stays in TMEM); also the NCHW output staging (2 x 64 x 256 bf16 at most)
 constexpr int OFF_OUTST = OFF_QRING;
 static_assert(QRING * QSLOT_BYTES >= 2 * 64 * 256 * 2, "the NCHW output staging lives in the QKV ring");
 static_assert(QRING >= 6 && QRING < 8, "one head-full barrier per head parity needs 6 or 7 sub-slots (see qkv_producer_main)");
-constexpr int OFF_XCH = OFF_QRING + QRING * QSLOT_BYTES;               // row exchange [2][128][4] floats
-static_assert(OFF_XCH - OFF_Q == RING * SLOT_BYTES, "the nine MLP ring slots tile [OFF_Q, OFF_XCH) exactly");
+constexpr int QRING_END = OFF_QRING + QRING * QSLOT_BYTES;
+constexpr int OFF_XCH = QRING_END > OFF_Q + RING * SLOT_BYTES ? QRING_END : OFF_Q + RING * SLOT_BYTES;      // row exchange [2][128][4] floats
+static_assert(OFF_XCH - OFF_Q >= RING * SLOT_BYTES, "the nine MLP ring slots fit in [OFF_Q, OFF_XCH)");
 static_assert(OFF_RING == OFF_Q + RING_LO * SLOT_BYTES, "ring slots are contiguous from OFF_Q");
 __host__ __device__ constexpr int slot_offset(uint32_t s) { return OFF_Q + int(s) * SLOT_BYTES; }
 constexpr int OFF_VEC = OFF_XCH + 2 * 128 * 4 * 4;      // per-layer vectors
