@@ -96,3 +96,42 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read(), f"{f} mentions the oracle"
+
+
+def test_graph_weight_signature_watches_the_hot_path_cheaply():
+    """GraphedHotPath runs this check on the host in front of every replay (graphs.py): it has to notice in-place edits,
+    load_state_dict and replaced Parameter objects of the hot path's modules, ignore the conv backbones (not read by the captured
+    kernels), and stay far below the 1.08 ms of the GPU step it precedes — the full-model scan took 0.9 ms and made the replay loop
+    host-bound."""
+    import time
+    from avformer_b200.graphs import hot_path_modules, weights_signature
+    m = A.TwoStreamAuralVisualFormer(video_pretrained=False, audio_pretrained=False, task="AU").eval()
+    watch = hot_path_modules(m)
+    vm = m.video_model.video_model
+    sig = weights_signature(m, watch)
+    assert weights_signature(m, watch) == sig
+    with torch.no_grad():
+        vm.s_former.conv1.weight.mul_(1.0)                 # conv trunk inside the SFormer wrapper: outside the hot path
+    assert weights_signature(m, watch) == sig
+    assert weights_signature(m) != weights_signature(m, watch)   # the full scan covers more tensors
+    full = weights_signature(m)
+    with torch.no_grad():
+        vm.s_former.conv1.weight.mul_(1.0)
+    assert weights_signature(m) != full                     # ... and sees the conv edit (InferenceEngine relies on it)
+    changes = []
+    with torch.no_grad():
+        vm.t_former.pos_embedding.add_(0.0)                 # in-place edit
+    changes.append(weights_signature(m, watch))
+    m.au_head.load_state_dict(m.au_head.state_dict())       # copy_ into every parameter of the fusion head
+    changes.append(weights_signature(m, watch))
+    lin = m.video_model.au_head.AU_linear_p3
+    lin.weight = torch.nn.Parameter(lin.weight.detach().clone())          # a replaced Parameter object
+    changes.append(weights_signature(m, watch))
+    m.audio_model.au_head.AU_BN1.running_mean.add_(0.0)     # a buffer
+    changes.append(weights_signature(m, watch))
+    assert len({sig, *changes}) == 5
+    t0 = time.perf_counter()
+    for _ in range(20):
+        weights_signature(m, watch)
+    per_call = (time.perf_counter() - t0) / 20
+    assert per_call < 0.5e-3, f"{per_call * 1e6:.0f} us per call"
