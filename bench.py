@@ -653,7 +653,7 @@ def run_train(model, A, dev, rank, world, args):
                      "peak_source": f"{peaks['source']} (sustained: a kernel chain timed inside a long step)", "algorithmic_flop_per_launch": flops_step},
         "cpu_baseline": cpu_baseline,
         "grad_bucket_bytes": bucket_bytes, "grad_allreduce": ("per-stack segments, asynchronous, started from the backward bridges (dp.SegmentReducer, NCCL)" if opt.overlap else
-                                                               ("one kernel over NVLink peer memory behind the backward (avf_grad_allreduce: two-shot, in place, deterministic)" if opt._buckets[0].get("peer") is not None
+                                                               ("summed over ranks AND applied by ONE kernel over NVLink peer memory behind the backward (avf_adam_allreduce_step: two-shot all-reduce, in place, deterministic, then Adam on the replicated bucket)" if opt._buckets[0].get("peer") is not None
                                                                 else "one NCCL all-reduce of the flat bucket behind the backward")) if world > 1 else None,
         "grad_allreduce_note": opt.reduce_note,
         "final_loss": final_loss,
@@ -734,6 +734,15 @@ def run_dp_check(model, A, dev, rank, world):
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         res["grad_peer_identical_on_all_ranks"] = bool(torch.equal(hi, lo))
+        # adam_allreduce_step: reduction + Adam as one kernel against reduction, then avf_adam_step, on copies of the live buckets
+        hyper = (5e-4, 0.9, 0.999, 1e-8, 5e-5)
+        pa, ma, va = bucket["p"].clone(), torch.zeros_like(bucket["p"]), torch.zeros_like(bucket["p"])
+        A.functional.adam_step_(pa, bucket["g"], ma, va, 1, *hyper, grad_scale=1.0 / world)
+        grads(*mine, reduce=False)                   # the same local gradients again (the backward is deterministic)
+        pb, mb, vb = bucket["p"].clone(), torch.zeros_like(bucket["p"]), torch.zeros_like(bucket["p"])
+        peer.reduce_adam_(pb, mb, vb, 1, *hyper)
+        peer.check()
+        res["adam_allreduce_fused_bit_identical"] = bool(torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and not torch.equal(pb, bucket["p"]))
     else:
         res["grad_peer_note"] = opt.reduce_note
     if rank == 0:
@@ -749,7 +758,8 @@ def run_dp_check(model, A, dev, rank, world):
         res["grad_max_rel_err"] = worst
         res["grad_segments_reduced_in_order"] = launched
         res["ok"] = bool(res["logits_max_abs_diff"] <= 1e-5 and worst < 2e-3
-                         and (peer is None or (res["grad_peer_vs_nccl_max_rel"] < 1e-5 and res["grad_peer_identical_on_all_ranks"])))
+                         and (peer is None or (res["grad_peer_vs_nccl_max_rel"] < 1e-5 and res["grad_peer_identical_on_all_ranks"]
+                                              and res["adam_allreduce_fused_bit_identical"])))
         print(json.dumps(res))
     ok = torch.tensor([1 if (rank != 0 or res.get("ok")) else 0], device=dev)
     if world > 1:

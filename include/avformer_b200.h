@@ -222,6 +222,15 @@ int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_
 size_t avf_peer_allreduce_bytes(int32_t world, size_t n_floats);
 int avf_grad_allreduce(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns, void* stream);
 
+/* `adam_allreduce_step` of SURVEY.md section 8(b): the reduction above and the optimiser step of train.py:235-236 (torch.optim.Adam with
+ * coupled L2, train.py:334; decoupled != 0 = AdamW) as ONE kernel — as soon as the sums of all slices are in this rank's bucket every CTA
+ * updates its share of the replicated parameters (params / exp_avg / exp_avg_sq: flat fp32 buckets of n_floats, a multiple of 4, 16-byte
+ * aligned; bf16_shadow: optional bf16 image of the updated parameters).  grad_scale is applied to the summed gradient (1 / world for the
+ * mean over shards); step is 1-based (bias correction).  Bit-identical to avf_grad_allreduce followed by avf_adam_step. */
+int avf_adam_allreduce_step(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns,
+                            float* params, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, int32_t step, int decoupled, float grad_scale, void* stream);
+
 /* ---- parameter preparation ------------------------------------------------------------------ */
 int avf_cast_f32_to_bf16(const float* src, void* dst, size_t n, void* stream);
 int avf_cast_bf16_to_f32(const void* src, float* dst, size_t n, void* stream);

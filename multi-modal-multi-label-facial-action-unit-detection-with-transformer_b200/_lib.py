@@ -86,6 +86,8 @@ SIGNATURES = {
     "avf_logits_wait": (ctypes.c_int, [_c_p, _sz, _i32, _c_p, ctypes.c_uint64, _c_p]),
     "avf_peer_allreduce_bytes": (_sz, [_i32, _sz]),
     "avf_grad_allreduce": (ctypes.c_int, [_c_p, _sz, _i32, _i32, _c_p, ctypes.c_uint64, _c_p]),
+    "avf_adam_allreduce_step": (ctypes.c_int, [_c_p, _sz, _i32, _i32, _c_p, ctypes.c_uint64, _c_p, _c_p, _c_p, _c_p] + [ctypes.c_float] * 5
+                                + [_i32, ctypes.c_int, ctypes.c_float, _c_p]),
     "avf_cast_f32_to_bf16": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_cast_bf16_to_f32": (ctypes.c_int, [_c_p, _c_p, _sz, _c_p]),
     "avf_add_row_periodic": (ctypes.c_int, [_c_p, _i32, _c_p, _i32, _i32, _i32, _c_p]),

@@ -394,6 +394,17 @@ int avf_grad_allreduce(const uint64_t* peer_base, size_t n_floats, int32_t world
   return grad_allreduce(reinterpret_cast<const unsigned long long*>(peer_base), n_floats, world, rank, state, timeout_ns, static_cast<cudaStream_t>(stream));
 }
 
+int avf_adam_allreduce_step(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns, float* params,
+                            float* exp_avg, float* exp_avg_sq, void* bf16_shadow, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                            int decoupled, float grad_scale, void* stream) {
+  int e = require_device();
+  if (e) return e;
+  AVF_REQUIRE(peer_base && state, AVF_EINVAL, "adam_allreduce_step: null pointer");
+  AVF_REQUIRE(world > 0 && world <= 16 && rank >= 0 && rank < world && n_floats > 0, AVF_EINVAL, "adam_allreduce_step: world %d (1..16) rank %d n %zu", world, rank, n_floats);
+  return adam_allreduce_step(reinterpret_cast<const unsigned long long*>(peer_base), n_floats, world, rank, state, timeout_ns, params, exp_avg, exp_avg_sq, bf16_shadow,
+                             lr, beta1, beta2, eps, weight_decay, step, decoupled, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
 int avf_au_confusion_update(const float* pred, int32_t ld_pred, float threshold, const float* labels, int32_t ld_labels, float ignore,
                             uint64_t* counts48, int32_t n_rows, void* stream) {
   int e = require_device();

@@ -17,7 +17,9 @@
 // Two slots are enough: A pushes step i+2 only after its wait of step i+1, which saw B's push of step i+1, which B issued (stream
 // order) after everything B did with the table of step i.  The spin is bounded (timeout -> error word, never a hung GPU).
 #include <algorithm>
+#include <cmath>
 
+#include "avf_adam.cuh"
 #include "avf_common.cuh"
 #include "avf_internal.h"
 
@@ -108,9 +110,19 @@ constexpr int AR_THREADS = 256;
 constexpr int AR_MAX_WORLD = 16;
 
 // state: [0] sequence number of the last completed reduction, [1] error word, [2] CTAs of this launch that finished their slice
-template <int W>
+// The optimiser step that follows the reduction, fused into the same kernel (avf_adam_allreduce_step): once the sums of all slices have
+// landed in this rank's bucket every CTA runs the Adam update of its share of the WHOLE bucket (weights are replicated: every rank
+// updates all of them, with identical inputs and therefore identical results).
+struct FusedAdam {
+  float *p, *m, *v;
+  __nv_bfloat16* shadow;
+  size_t n;              // elements of the bucket that carry parameters (n <= n_pad)
+  AdamParams a;
+};
+
+template <int W, bool ADAM>
 __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsigned long long* __restrict__ peer_base, size_t n_pad, int world_rt, int rank,
-                                                                    uint32_t* state, unsigned long long timeout_ns) {
+                                                                    uint32_t* state, unsigned long long timeout_ns, FusedAdam ad) {
   const int world = W > 0 ? W : world_rt;
   const uint32_t seq = state[0] + 1u;
   __shared__ unsigned long long base[AR_MAX_WORLD];
@@ -171,10 +183,31 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
       for (int p = 0; p < world; ++p) st_release_sys_u32(reinterpret_cast<uint32_t*>(base[p] + flag_off) + world + rank, seq);
     }
   }
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 || ADAM) {
     if (int(threadIdx.x) < world && !spin_until(my_exit + threadIdx.x, seq, timeout_ns)) atomicCAS(&state[1], 0u, 101u + threadIdx.x);
     __syncthreads();
-    if (threadIdx.x == 0) state[0] = seq;
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = seq;
+  }
+  if constexpr (ADAM) {
+    // (4) Adam over the whole (now summed) bucket; 16-byte groups, the bucket length is a multiple of 4 (FusedAdam pads every parameter to 8)
+    const float4* g4 = reinterpret_cast<const float4*>(base[rank]);
+    float4 *p4 = reinterpret_cast<float4*>(ad.p), *m4 = reinterpret_cast<float4*>(ad.m), *v4 = reinterpret_cast<float4*>(ad.v);
+    for (size_t i = size_t(blockIdx.x) * AR_THREADS + threadIdx.x; i < ad.n / 4; i += size_t(gridDim.x) * AR_THREADS) {
+      const float4 g = __ldcg(g4 + i);
+      float4 pv = p4[i], mv = m4[i], vv = v4[i];
+      adam_update(pv.x, g.x, mv.x, vv.x, ad.a);
+      adam_update(pv.y, g.y, mv.y, vv.y, ad.a);
+      adam_update(pv.z, g.z, mv.z, vv.z, ad.a);
+      adam_update(pv.w, g.w, mv.w, vv.w, ad.a);
+      p4[i] = pv; m4[i] = mv; v4[i] = vv;
+      if (ad.shadow != nullptr) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(ad.shadow)[i] = o;
+      }
+    }
   }
 }
 
@@ -183,21 +216,57 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
 size_t peer_allreduce_pad(int world, size_t n) { return (n + size_t(4) * world - 1) / (size_t(4) * world) * (size_t(4) * world); }
 size_t peer_allreduce_bytes(int world, size_t n) { return peer_allreduce_pad(world, n) * sizeof(float) + size_t(2) * world * sizeof(uint32_t); }
 
-int grad_allreduce(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, cudaStream_t st) {
+namespace {
+template <bool ADAM>
+int launch_allreduce(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, const FusedAdam& ad,
+                     cudaStream_t st) {
   const size_t n_pad = peer_allreduce_pad(world, n);
   const size_t slice4 = n_pad / 4 / world;
-  // two CTAs per SM: ptxas keeps four of a thread's eight 16-byte loads in flight at a time, so the bytes in flight (2 x 148 x 256 x 64 B =
-  // 4.8 MB) come from the CTA count; all of them are co-resident (<= 128 registers, 128 B of shared memory), as the flag protocol needs
-  int grid = int(std::min<size_t>(size_t(2 * sm_count_of_current_device()), (slice4 + AR_THREADS - 1) / AR_THREADS));
+  // Up to two CTAs per SM: ptxas keeps four of a thread's eight 16-byte loads in flight at a time, so the bytes in flight (2 x 148 x 256 x
+  // 64 B = 4.8 MB) come from the CTA count.  ALL CTAs must be co-resident — the last one to finish its slice releases the exit flags the
+  // others (all of them in the fused-Adam form) spin on — so the grid is bounded by what the occupancy calculator says fits at once.
+  int per_sm = 0;
+  const void* fn = nullptr;
+  switch (world) {
+    case 2: fn = reinterpret_cast<const void*>(&grad_allreduce_kernel<2, ADAM>); break;
+    case 4: fn = reinterpret_cast<const void*>(&grad_allreduce_kernel<4, ADAM>); break;
+    case 8: fn = reinterpret_cast<const void*>(&grad_allreduce_kernel<8, ADAM>); break;
+    default: fn = reinterpret_cast<const void*>(&grad_allreduce_kernel<0, ADAM>); break;
+  }
+  AVF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, AR_THREADS, 0));
+  AVF_REQUIRE(per_sm >= 1, AVF_EINVAL, "grad_allreduce: the kernel does not fit on an SM");
+  const size_t want = ADAM ? std::max<size_t>((slice4 + AR_THREADS - 1) / AR_THREADS, (ad.n / 4 + AR_THREADS - 1) / AR_THREADS) : (slice4 + AR_THREADS - 1) / AR_THREADS;
+  int grid = int(std::min<size_t>(size_t(std::min(per_sm, 2) * sm_count_of_current_device()), want));
   if (grid < 1) grid = 1;
   switch (world) {
-    case 2: grad_allreduce_kernel<2><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
-    case 4: grad_allreduce_kernel<4><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
-    case 8: grad_allreduce_kernel<8><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
-    default: grad_allreduce_kernel<0><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns); break;
+    case 2: grad_allreduce_kernel<2, ADAM><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns, ad); break;
+    case 4: grad_allreduce_kernel<4, ADAM><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns, ad); break;
+    case 8: grad_allreduce_kernel<8, ADAM><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns, ad); break;
+    default: grad_allreduce_kernel<0, ADAM><<<grid, AR_THREADS, 0, st>>>(peer_base, n_pad, world, rank, state, timeout_ns, ad); break;
   }
   AVF_LAUNCH_CHECK("grad_allreduce_kernel");
   return 0;
+}
+}  // namespace
+
+int grad_allreduce(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, cudaStream_t st) {
+  return launch_allreduce<false>(peer_base, n, world, rank, state, timeout_ns, FusedAdam{}, st);
+}
+
+// All-reduce (sum) of the peer-mapped gradient buckets + Adam / AdamW on the replicated parameters in ONE kernel; grad_scale = 1 / world
+// (the mean of the data-parallel shards) unless the caller says otherwise.
+int adam_allreduce_step(const unsigned long long* peer_base, size_t n, int world, int rank, uint32_t* state, unsigned long long timeout_ns, float* p, float* m,
+                        float* v, void* shadow, float lr, float b1, float b2, float eps, float wd, int step, int decoupled, float grad_scale, cudaStream_t st) {
+  AVF_REQUIRE(p && m && v, AVF_EINVAL, "adam_allreduce_step: null pointer");
+  AVF_REQUIRE(step >= 1, AVF_EINVAL, "adam_allreduce_step: step=%d (1-based)", step);
+  AVF_REQUIRE((n & 3u) == 0, AVF_EINVAL, "adam_allreduce_step: bucket length %zu is not a multiple of 4", n);
+  AVF_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(shadow)) & 15) == 0,
+              AVF_EINVAL, "adam_allreduce_step: buckets must be 16-byte aligned");
+  const double bc1 = 1.0 - pow(double(b1), step), bc2 = 1.0 - pow(double(b2), step);
+  FusedAdam ad;
+  ad.p = p; ad.m = m; ad.v = v; ad.shadow = static_cast<__nv_bfloat16*>(shadow); ad.n = n;
+  ad.a = AdamParams{lr, b1, b2, eps, wd, float(1.0 / bc1), float(1.0 / sqrt(bc2)), grad_scale, decoupled};
+  return launch_allreduce<true>(peer_base, n, world, rank, state, timeout_ns, ad, st);
 }
 
 size_t peer_gather_bytes(int world, size_t n) { return peer_flags_offset(world, n) + size_t(2) * world * sizeof(uint32_t); }

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "avf_adam.cuh"
 #include "avf_common.cuh"
 #include "avf_internal.h"
 
@@ -488,15 +489,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     for (int j = 0; j < cnt; ++j) { pv[j] = p[i + j]; gv[j] = g[i + j]; mv[j] = m[i + j]; vv[j] = v[i + j]; }
   }
 #pragma unroll
+  const AdamParams ap{lr, b1, b2, eps, wd, inv_bc1, inv_sqrt_bc2, grad_scale, decoupled};
   for (int j = 0; j < 4; ++j) {
     if (j >= cnt) break;
-    float gr = gv[j] * grad_scale;
-    if (decoupled) pv[j] *= 1.f - lr * wd;
-    else gr = fmaf(wd, pv[j], gr);
-    mv[j] = b1 * mv[j] + (1.f - b1) * gr;
-    vv[j] = b2 * vv[j] + (1.f - b2) * gr * gr;
-    const float denom = sqrtf(vv[j]) * inv_sqrt_bc2 + eps;
-    pv[j] -= lr * inv_bc1 * (mv[j] / denom);
+    adam_update(pv[j], gv[j], mv[j], vv[j], ap);
   }
   if (full) {
     *reinterpret_cast<float4*>(p + i) = make_float4(pv[0], pv[1], pv[2], pv[3]);

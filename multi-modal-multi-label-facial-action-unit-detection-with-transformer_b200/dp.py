@@ -3,7 +3,7 @@ the batch, weights are replicated, and the only collectives are the logit gather
 gradient all-reduce in training.  torch.distributed (NCCL on GPUs, gloo in CPU tests) is the transport."""
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -198,6 +198,19 @@ class PeerAllReduce:
         self._L.check(self._L.lib().avf_grad_allreduce(c(self.peer_base.data_ptr()), self.n, self.world, self.rank, c(self.state.data_ptr()),
                                                        self.timeout_ns, c(torch.cuda.current_stream().cuda_stream)), "avf_grad_allreduce")
         return self.grad
+
+    def reduce_adam_(self, p: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float, beta1: float, beta2: float, eps: float,
+                     weight_decay: float, decoupled: bool = False, grad_scale: Optional[float] = None, shadow: Optional[torch.Tensor] = None) -> None:
+        """reduce_() and the Adam / AdamW step on the replicated flat parameter bucket as ONE kernel (avf_adam_allreduce_step):
+        bit-identical to reduce_() followed by functional.adam_step_ with grad_scale = 1 / world."""
+        if not (p.numel() == m.numel() == v.numel() == self.n and self.n % 4 == 0):
+            raise ValueError("PeerAllReduce.reduce_adam_: parameter / moment buckets must have the gradient bucket's length (a multiple of 4)")
+        c = self._ct.c_void_p
+        gs = (1.0 / self.world) if grad_scale is None else float(grad_scale)
+        self._L.check(self._L.lib().avf_adam_allreduce_step(
+            c(self.peer_base.data_ptr()), self.n, self.world, self.rank, c(self.state.data_ptr()), self.timeout_ns, c(p.data_ptr()), c(m.data_ptr()),
+            c(v.data_ptr()), c(shadow.data_ptr()) if shadow is not None else None, lr, beta1, beta2, eps, weight_decay, int(step), int(decoupled), gs,
+            c(torch.cuda.current_stream().cuda_stream)), "avf_adam_allreduce_step")
 
     def check(self) -> int:
         """Synchronise; raise if a peer never showed up; return the number of completed reductions."""

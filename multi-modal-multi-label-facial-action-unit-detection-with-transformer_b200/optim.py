@@ -264,13 +264,21 @@ class FusedAdam(torch.optim.Optimizer):
             if world > 1 and self._reducer is not None and self._reducer.armed:
                 self._reducer.finish()                            # segments were armed for this backward pass: reduce / join what is left
                 self._reducer.disarm()
+                fused = False
             elif world > 1 and b.get("peer") is not None:
-                b["peer"].reduce_()                               # one kernel over NVLink peer memory, in place
+                fused = True                                      # the sum over ranks AND the update: one kernel over NVLink peer memory
             elif world > 1:
                 dist.all_reduce(b["g"], op=dist.ReduceOp.SUM, group=self.process_group)
+                fused = False
+            else:
+                fused = False
             b["step"] += 1
-            AF.adam_step_(b["p"], b["g"], b["m"], b["v"], b["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
-                          group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world, shadow=b["shadow"])
+            if fused:
+                b["peer"].reduce_adam_(b["p"], b["m"], b["v"], b["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                                       group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world, shadow=b["shadow"])
+            else:
+                AF.adam_step_(b["p"], b["g"], b["m"], b["v"], b["step"], group["lr"], group["betas"][0], group["betas"][1], group["eps"],
+                              group["weight_decay"], decoupled=group["decoupled"], grad_scale=1.0 / world, shadow=b["shadow"])
             # GEMM operand copies for free: weight matrices point at their bf16 image in the shadow bucket, valid for exactly this
             # parameter version (load_state_dict / manual edits bump the version and fall back to the cast kernel)
             for p, sview in b["mats"]:

@@ -478,6 +478,27 @@ def test_graphed_hot_path_with_the_logit_gather_inside_the_graph():
         ar.reduce_()
         ar.reduce_()
         assert ar.check() == 2 and torch.equal(ar.grad, before)
+        # adam_allreduce_step: the reduction and the Adam update as ONE kernel == reduce_() then avf_adam_step, bit for bit
+        n = 100000
+        ar2 = A.dp.PeerAllReduce(n)
+        g0 = torch.randn(n, device="cuda") * 1e-2
+        state0 = [torch.randn(n, device="cuda"), torch.randn(n, device="cuda") * 1e-3, torch.rand(n, device="cuda") * 1e-4]
+        hyper = dict(lr=5e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-5)
+        for decoupled in (False, True):
+            pa, ma, va = (t.clone() for t in state0)
+            sha = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+            ar2.grad.copy_(g0)
+            ar2.reduce_()
+            AF.adam_step_(pa, ar2.grad, ma, va, 3, hyper["lr"], hyper["beta1"], hyper["beta2"], hyper["eps"], hyper["weight_decay"], decoupled=decoupled,
+                          grad_scale=1.0, shadow=sha)
+            pb, mb, vb = (t.clone() for t in state0)
+            shb = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+            ar2.grad.copy_(g0)
+            ar2.reduce_adam_(pb, mb, vb, 3, decoupled=decoupled, shadow=shb, **hyper)
+            torch.cuda.synchronize()
+            assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb) and torch.equal(sha, shb)
+            assert not torch.equal(pb, state0[0])
+        assert ar2.check() == 4
         m.train()
         params = [q for q in m.au_head.parameters() if q.requires_grad]
         opt = A.FusedAdam(params, lr=1e-3)
