@@ -23,6 +23,8 @@ from .encoder import GELU, Attention, FeedForward, PreNorm, Residual, Transforme
 from .heads import AU_former, VA_former, former_AU_head, tformer_AU_head
 from .loss import AULoss
 from .metrics import MultiLabelAccF1
+from . import outputs
+from .outputs import AUResultWriter
 from .optim import FusedAdam
 from .graphs import GraphedHotPath, GraphedTrainStep
 from .inference import InferenceEngine
@@ -31,5 +33,5 @@ from .video import BasicBlock, Dummy, ResFormer, SFormerBlock, TFormer, VideoMod
 __all__ = [
     "TwoStreamAuralVisualFormer", "AudioFormer", "VisualFormer", "VideoModel", "ResFormer", "TFormer", "BasicBlock", "Dummy",
     "AU_former", "VA_former", "SFormerBlock", "former_AU_head", "tformer_AU_head", "Transformer", "Attention", "FeedForward", "PreNorm", "Residual", "GELU",
-    "AULoss", "MultiLabelAccF1", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "InferenceEngine", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
+    "AULoss", "MultiLabelAccF1", "AUResultWriter", "outputs", "AudioModel", "FusedAdam", "GraphedHotPath", "GraphedTrainStep", "InferenceEngine", "graphs", "dp", "functional", "autograd", "optim", "build", "set_default_precision", "default_precision", "load_pretrain",
 ]
