@@ -218,7 +218,8 @@ int avf_logits_wait(const void* my_base, size_t n_floats, int32_t world, uint32_
  * as mapped here; state = three DEVICE words zeroed once ([0] completed reductions, [1] error: 1 + r / 101 + r = rank r missing at
  * entry / exit, [2] scratch).  avf_grad_allreduce sums the buckets of all ranks IN PLACE (every rank ends with the same bits: slice r
  * is added up by rank r in rank order 0..W-1 and stored into all buckets); asynchronous on `stream`, graph-capturable, to be issued
- * once per step on every rank; bounded spins (timeout_ns).  world <= 16, one node. */
+ * once per step on every rank; bounded spins: after timeout_ns the kernel records the missing rank in state[1], prints it and traps
+ * (unsummed gradients never reach the optimiser silently).  world <= 16, one node. */
 size_t avf_peer_allreduce_bytes(int32_t world, size_t n_floats);
 int avf_grad_allreduce(const uint64_t* peer_base, size_t n_floats, int32_t world, int32_t rank, uint32_t* state, uint64_t timeout_ns, void* stream);
 

@@ -91,7 +91,7 @@ __global__ void logits_wait_kernel(const uint8_t* __restrict__ my_base, size_t n
 // buckets (16-byte loads straight from the peers' memory, ranks added in the fixed order 0..W-1, so the result is deterministic and
 // identical everywhere) and stores the sum into slice r of ALL buckets; (3) tell every peer "my slice is in your bucket, I have stopped
 // reading yours" and wait for theirs.  Per GPU (W-1)/W of the bucket crosses NVLink once in each direction and nothing is staged,
-// against NCCL's ring / tree of the same 41.7 MB at 0.25 ms on 8 B200s.  Spins are bounded (timeout -> error word).
+// against NCCL's ring / tree of the same 41.7 MB at 0.25 ms on 8 B200s.  Spins are bounded (timeout -> error word, message, trap).
 // Bucket loads: weak ld.global.cg (L2 only).  They are ordered behind the acquire of the peers' "bucket complete" flags (ld.acquire.sys
 // + bar.sync), which is all the memory model asks for, and — unlike volatile / .relaxed.sys loads, which ptxas issued in dependent
 // groups of 4 + 2 + 2 — the eight of them go out back to back, one NVLink round trip per element.
@@ -104,6 +104,15 @@ __device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t seq, u
     if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) return false;
   }
   return true;
+}
+
+// A peer that never shows up: gradients that were not summed must not reach the optimiser silently.  Record who was missing, say so,
+// and stop the kernel with an error the host sees at its next synchronisation (the training step cannot be saved anyway).
+__device__ __noinline__ void give_up(uint32_t* state, uint32_t code, int rank, const char* where) {
+  atomicCAS(&state[1], 0u, code);
+  __threadfence_system();
+  printf("avf: gradient all-reduce on rank %d: rank %u did not reach the %s of the reduction in time\n", rank, (code - 1u) % 100u, where);
+  __trap();
 }
 
 constexpr int AR_THREADS = 256;
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
     __threadfence_system();
     st_release_sys_u32(reinterpret_cast<uint32_t*>(base[threadIdx.x] + flag_off) + rank, seq);
   }
-  if (int(threadIdx.x) < world && !spin_until(my_enter + threadIdx.x, seq, timeout_ns)) atomicCAS(&state[1], 0u, 1u + threadIdx.x);
+  if (int(threadIdx.x) < world && !spin_until(my_enter + threadIdx.x, seq, timeout_ns)) give_up(state, 1u + threadIdx.x, rank, "entry");
   __syncthreads();
 
   // (2) reduce my slice of all buckets, store it everywhere
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(AR_THREADS) grad_allreduce_kernel(const unsign
     }
   }
   if (blockIdx.x == 0 || ADAM) {
-    if (int(threadIdx.x) < world && !spin_until(my_exit + threadIdx.x, seq, timeout_ns)) atomicCAS(&state[1], 0u, 101u + threadIdx.x);
+    if (int(threadIdx.x) < world && !spin_until(my_exit + threadIdx.x, seq, timeout_ns)) give_up(state, 101u + threadIdx.x, rank, "exit");
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = seq;
   }

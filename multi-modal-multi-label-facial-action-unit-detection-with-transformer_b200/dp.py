@@ -213,7 +213,8 @@ class PeerAllReduce:
             c(torch.cuda.current_stream().cuda_stream)), "avf_adam_allreduce_step")
 
     def check(self) -> int:
-        """Synchronise; raise if a peer never showed up; return the number of completed reductions."""
+        """Synchronise and return the number of completed reductions.  (A peer that never shows up makes the kernel trap after its
+        timeout, which surfaces here or at any earlier synchronisation as a CUDA error; the error word is checked as well.)"""
         torch.cuda.synchronize()
         done, err = (int(v) for v in self.state[:2].tolist())
         if err != 0:
